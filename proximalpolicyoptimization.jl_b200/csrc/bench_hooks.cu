@@ -1,0 +1,236 @@
+// bench_hooks.cu — ppo_bench_kernel: time ONE kernel of the hot path in isolation on a synthetic,
+// device-resident problem (CUDA events on the ctx stream, optional L2 flush between launches).
+// Used by bench.py for the per-kernel roofline numbers; not part of the reference-facing API.
+#include <string.h>
+
+#include <string>
+
+#include "common.cuh"
+#include "gemm_tc.cuh"
+
+namespace ppo {
+namespace {
+
+__device__ __forceinline__ uint32_t hash32(uint64_t x) {
+    x ^= x >> 33; x *= 0xff51afd7ed558ccdull; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ull; x ^= x >> 33;
+    return (uint32_t)x;
+}
+
+// kind 0: uniform [-1,1) floats; 1: small integer rewards [-4,4]; 2: mask (0 / -inf, p=.25 per group of 16,
+// group 0 of each row of `row` elements unmasked); 3: probabilities in (0.05, 1]
+__global__ void fill_f32_kernel(float* p, int64_t n, int kind, int row, uint64_t seed) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        uint32_t h = hash32(i * 0x9E3779B97F4A7C15ull + seed);
+        float u = (float)(h >> 8) * (1.0f / 16777216.0f);
+        float v;
+        if (kind == 0) v = 2.0f * u - 1.0f;
+        else if (kind == 1) v = (float)((int)(h % 9u) - 4);
+        else if (kind == 2) {
+            int64_t col = i % row, grp = col / 16;
+            uint32_t hg = hash32((uint64_t)((i / row) * 4096 + grp) * 0x9E3779B97F4A7C15ull + seed);
+            v = (grp != 0 && (hg & 3u) == 0u) ? -INFINITY : 0.0f;
+        } else v = 0.05f + 0.95f * u;
+        p[i] = v;
+    }
+}
+__global__ void fill_terminal_kernel(uint8_t* t, int64_t n, int mean_len, uint64_t seed) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        t[i] = (hash32(i * 0x9E3779B97F4A7C15ull + seed) % (uint32_t)mean_len) == 0u || i == n - 1;
+}
+__global__ void fill_zero_i32_kernel(int* p, int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        p[i] = 0;
+}
+
+struct Scope {  // frees everything on exit
+    std::vector<void*> ptrs;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    ~Scope() {
+        for (void* p : ptrs) cudaFree(p);
+        if (e0) cudaEventDestroy(e0);
+        if (e1) cudaEventDestroy(e1);
+    }
+    template <typename T>
+    int alloc(T** p, size_t count) {
+        *p = nullptr;
+        PPO_CUDA(cudaMalloc((void**)p, (count ? count : 1) * sizeof(T)));
+        ptrs.push_back(*p);
+        return PPO_OK;
+    }
+};
+
+int fill(ppo_ctx* ctx, float* p, int64_t n, int kind, int row, uint64_t seed) {
+    fill_f32_kernel<<<(unsigned)std::min<int64_t>(ceil_div(n, 256), 148 * 16), 256, 0, ctx->stream>>>(p, n, kind, row, seed);
+    PPO_CUDA(cudaGetLastError());
+    return PPO_OK;
+}
+
+template <typename F>
+int time_loop(ppo_ctx* ctx, Scope& sc, int iters, int flush, F&& launch, double* ms_out) {
+    PPO_CUDA(cudaEventCreate(&sc.e0));
+    PPO_CUDA(cudaEventCreate(&sc.e1));
+    for (int w = 0; w < 3; ++w) PPO_TRY(launch());
+    PPO_CUDA(cudaStreamSynchronize(ctx->stream));
+    double total = 0.0;
+    for (int it = 0; it < iters; ++it) {
+        if (flush) PPO_TRY(flush_l2(ctx));
+        PPO_CUDA(cudaEventRecord(sc.e0, ctx->stream));
+        PPO_TRY(launch());
+        PPO_CUDA(cudaEventRecord(sc.e1, ctx->stream));
+        PPO_CUDA(cudaEventSynchronize(sc.e1));
+        float ms = 0.0f;
+        PPO_CUDA(cudaEventElapsedTime(&ms, sc.e0, sc.e1));
+        total += ms;
+    }
+    *ms_out = total / iters;
+    return PPO_OK;
+}
+
+}  // namespace
+}  // namespace ppo
+
+using namespace ppo;
+
+extern "C" int ppo_bench_kernel(ppo_ctx* ctx, const char* which, int64_t n, int a, int b, int c, int iters,
+                                int flush_l2_flag, double* ms_out, double* work_out) {
+    PPO_REQUIRE(ctx && which && ms_out && work_out, "bench_kernel: null argument");
+    PPO_CUDA(cudaSetDevice(ctx->device));
+    PPO_REQUIRE(n >= 1 && iters >= 1, "bench_kernel: n=%lld iters=%d", (long long)n, iters);
+    Scope sc;
+    const std::string w(which);
+    if (w == "scan") {
+        float* r; uint8_t* t; double* stats;
+        const int64_t n16 = round_up(n, SCAN_TILE);
+        PPO_TRY(sc.alloc(&r, (size_t)n16)); PPO_TRY(sc.alloc(&t, (size_t)n16));
+        PPO_TRY(sc.alloc(&stats, (size_t)2 * ceil_div(n, SCAN_TILE)));
+        void* scratch; PPO_TRY(sc.alloc((char**)&scratch, scan_scratch_bytes(n)));
+        PPO_TRY(fill(ctx, r, n, 1, 1, 11));
+        fill_terminal_kernel<<<148 * 8, 256, 0, ctx->stream>>>(t, n, a > 0 ? a : 15, 12);
+        const double disc = (b == 0) ? 1.0 : 0.99;
+        // rewards are overwritten by returns every launch; with |r| <= 4 and episodes of ~a steps the values
+        // stay finite over the few launches timed here only if we refill: refill outside the timed region.
+        auto launch = [&]() -> int { return launch_returns_scan(ctx, r, t, n, disc, 0, stats, scratch); };
+        PPO_CUDA(cudaEventCreate(&sc.e0)); PPO_CUDA(cudaEventCreate(&sc.e1));
+        double total = 0.0;
+        for (int it = -3; it < iters; ++it) {
+            PPO_TRY(fill(ctx, r, n, 1, 1, 11));
+            if (flush_l2_flag) PPO_TRY(flush_l2(ctx));
+            PPO_CUDA(cudaEventRecord(sc.e0, ctx->stream));
+            PPO_TRY(launch());
+            PPO_CUDA(cudaEventRecord(sc.e1, ctx->stream));
+            PPO_CUDA(cudaEventSynchronize(sc.e1));
+            float ms = 0.0f; PPO_CUDA(cudaEventElapsedTime(&ms, sc.e0, sc.e1));
+            if (it >= 0) total += ms;
+        }
+        *ms_out = total / iters;
+        *work_out = 9.0 * (double)n;
+        return PPO_OK;
+    }
+    if (w == "shuffle") {
+        int* perm; PPO_TRY(sc.alloc(&perm, (size_t)n));
+        PPO_TRY(time_loop(ctx, sc, iters, flush_l2_flag, [&]() { return launch_feistel_permutation(ctx, perm, n, 77); }, ms_out));
+        *work_out = 4.0 * (double)n;
+        return PPO_OK;
+    }
+    if (w == "gather0" || w == "gather1") {
+        // n buffer rows, a = feature floats per row, b = mask floats per row, c = rows gathered per launch
+        const int64_t cnt = c;
+        PPO_REQUIRE(a >= 1 && b >= 1 && cnt >= 1 && cnt <= n, "bench gather: bad shape");
+        float *feat, *mask, *prob, *ret, *fo, *mo, *po, *ao; int *act, *perm, *acto;
+        PPO_TRY(sc.alloc(&feat, (size_t)n * a)); PPO_TRY(sc.alloc(&mask, (size_t)n * b));
+        PPO_TRY(sc.alloc(&prob, (size_t)n)); PPO_TRY(sc.alloc(&ret, (size_t)n)); PPO_TRY(sc.alloc(&act, (size_t)n));
+        PPO_TRY(sc.alloc(&perm, (size_t)n));
+        PPO_TRY(sc.alloc(&fo, (size_t)cnt * a)); PPO_TRY(sc.alloc(&mo, (size_t)cnt * b));
+        PPO_TRY(sc.alloc(&po, (size_t)cnt)); PPO_TRY(sc.alloc(&ao, (size_t)cnt)); PPO_TRY(sc.alloc(&acto, (size_t)cnt));
+        PPO_TRY(fill(ctx, feat, n * a, 0, 1, 1)); PPO_TRY(fill(ctx, mask, n * b, 2, b, 2));
+        PPO_TRY(fill(ctx, prob, n, 3, 1, 3)); PPO_TRY(fill(ctx, ret, n, 1, 1, 4));
+        fill_zero_i32_kernel<<<148 * 8, 256, 0, ctx->stream>>>(act, n);
+        PPO_TRY(launch_feistel_permutation(ctx, perm, n, 5));
+        GatherArgs g{};
+        g.feat = feat; g.mask = mask; g.action = act; g.old_prob = prob; g.ret = ret; g.count = cnt;
+        g.feat_elems = a; g.mask_elems = b; g.feat_out = fo; g.mask_out = mo; g.action_out = acto; g.prob_out = po;
+        g.adv_out = ao; g.norm = nullptr;
+        int64_t pos = 0;
+        const int variant = (w == "gather1") ? 1 : 0;
+        auto launch = [&]() -> int {
+            g.index = perm + pos;
+            pos = (pos + cnt + cnt <= n) ? pos + cnt : 0;   // walk through the epoch's minibatches
+            return launch_gather(ctx, g, variant);
+        };
+        PPO_TRY(time_loop(ctx, sc, iters, flush_l2_flag, launch, ms_out));
+        *work_out = (double)cnt * (4.0 + 2.0 * (4.0 * a + 4.0 * b + 12.0));
+        return PPO_OK;
+    }
+    if (w == "loss") {
+        const int A = a; const int64_t nb = n;
+        float *lg, *mk, *old, *adv, *dl; int* act; double *part, *out;
+        PPO_TRY(sc.alloc(&lg, (size_t)nb * A)); PPO_TRY(sc.alloc(&mk, (size_t)nb * A)); PPO_TRY(sc.alloc(&dl, (size_t)nb * A));
+        PPO_TRY(sc.alloc(&old, (size_t)nb)); PPO_TRY(sc.alloc(&adv, (size_t)nb)); PPO_TRY(sc.alloc(&act, (size_t)nb));
+        PPO_TRY(sc.alloc(&part, (size_t)2 * loss_num_blocks(nb, A))); PPO_TRY(sc.alloc(&out, 2));
+        PPO_TRY(fill(ctx, lg, nb * A, 0, 1, 1)); PPO_TRY(fill(ctx, mk, nb * A, 2, A, 2));
+        PPO_TRY(fill(ctx, old, nb, 3, 1, 3)); PPO_TRY(fill(ctx, adv, nb, 1, 1, 4));
+        fill_zero_i32_kernel<<<148 * 8, 256, 0, ctx->stream>>>(act, nb);
+        auto launch = [&]() -> int {
+            return launch_loss(ctx, lg, mk, act, old, adv, nb, A, 0.05, 0.01, 1.0 / (double)nb, dl, part, out, nullptr);
+        };
+        PPO_TRY(time_loop(ctx, sc, iters, flush_l2_flag, launch, ms_out));
+        *work_out = (double)nb * (12.0 * A + 12.0);
+        return PPO_OK;
+    }
+    if (w == "adam") {
+        float *x, *m, *v, *g; double* bp;
+        PPO_TRY(sc.alloc(&x, (size_t)n)); PPO_TRY(sc.alloc(&m, (size_t)n)); PPO_TRY(sc.alloc(&v, (size_t)n));
+        PPO_TRY(sc.alloc(&g, (size_t)n)); PPO_TRY(sc.alloc(&bp, 2));
+        PPO_TRY(fill(ctx, x, n, 0, 1, 1)); PPO_TRY(fill(ctx, g, n, 0, 1, 2));
+        PPO_CUDA(cudaMemsetAsync(m, 0, (size_t)n * 4, ctx->stream)); PPO_CUDA(cudaMemsetAsync(v, 0, (size_t)n * 4, ctx->stream));
+        double h[2] = {0.9, 0.999};
+        PPO_CUDA(cudaMemcpyAsync(bp, h, 16, cudaMemcpyHostToDevice, ctx->stream));
+        PPO_CUDA(cudaStreamSynchronize(ctx->stream));
+        auto launch = [&]() -> int { return launch_adam(ctx, x, m, v, g, n, 1e-4, 0.9, 0.999, 1e-8, bp, 1.0f); };
+        PPO_TRY(time_loop(ctx, sc, iters, flush_l2_flag, launch, ms_out));
+        *work_out = 28.0 * (double)n;
+        return PPO_OK;
+    }
+    if (w == "head_fwd" || w == "head_bwd") {
+        const int64_t M = n; const int K = a, N = b;
+        float *H, *W, *bias, *lg, *dH, *dW, *db, *part;
+        PPO_TRY(sc.alloc(&H, (size_t)M * K)); PPO_TRY(sc.alloc(&W, (size_t)K * N)); PPO_TRY(sc.alloc(&bias, (size_t)N));
+        PPO_TRY(sc.alloc(&lg, (size_t)M * N)); PPO_TRY(sc.alloc(&dH, (size_t)M * K)); PPO_TRY(sc.alloc(&dW, (size_t)K * N));
+        PPO_TRY(sc.alloc(&db, (size_t)N));
+        const size_t pb = wgrad_partial_bytes(M, K, N);
+        PPO_TRY(sc.alloc((char**)&part, pb));
+        PPO_TRY(fill(ctx, H, M * K, 0, 1, 1)); PPO_TRY(fill(ctx, W, (int64_t)K * N, 0, 1, 2));
+        PPO_TRY(fill(ctx, bias, N, 0, 1, 3)); PPO_TRY(fill(ctx, lg, M * N, 0, 1, 4));
+        if (w == "head_fwd") {
+            PPO_TRY(time_loop(ctx, sc, iters, flush_l2_flag, [&]() { return launch_head_fwd(ctx, H, W, bias, lg, M, K, N); }, ms_out));
+            *work_out = (double)M * (4.0 * K + 4.0 * N);
+        } else {
+            PPO_TRY(time_loop(ctx, sc, iters, flush_l2_flag,
+                              [&]() { return launch_head_bwd(ctx, H, lg, W, dH, dW, db, M, K, N, 0.01f, part, pb, true); }, ms_out));
+            *work_out = (double)M * (8.0 * K + 4.0 * N);
+        }
+        return PPO_OK;
+    }
+    if (w == "gemm_fwd" || w == "gemm_dgrad" || w == "gemm_wgrad") {
+        // fp32 SIMT engine; the tensor-core engines are timed through "tc_*" below
+        const int64_t M = n; const int K = a, N = b;
+        float *X, *W, *bias, *Y, *dX, *dW, *db, *part;
+        PPO_TRY(sc.alloc(&X, (size_t)M * K)); PPO_TRY(sc.alloc(&W, (size_t)K * N)); PPO_TRY(sc.alloc(&bias, (size_t)N));
+        PPO_TRY(sc.alloc(&Y, (size_t)M * N)); PPO_TRY(sc.alloc(&dX, (size_t)M * K)); PPO_TRY(sc.alloc(&dW, (size_t)K * N));
+        PPO_TRY(sc.alloc(&db, (size_t)N));
+        const size_t pb = wgrad_partial_bytes(M, K, N);
+        PPO_TRY(sc.alloc((char**)&part, pb));
+        PPO_TRY(fill(ctx, X, M * K, 0, 1, 1)); PPO_TRY(fill(ctx, W, (int64_t)K * N, 0, 1, 2));
+        PPO_TRY(fill(ctx, bias, N, 0, 1, 3)); PPO_TRY(fill(ctx, Y, M * N, 0, 1, 4));
+        if (w == "gemm_fwd")
+            PPO_TRY(time_loop(ctx, sc, iters, flush_l2_flag, [&]() { return launch_linear_fwd_simt(ctx, X, W, bias, Y, M, K, N, true, 0.01f); }, ms_out));
+        else if (w == "gemm_dgrad")
+            PPO_TRY(time_loop(ctx, sc, iters, flush_l2_flag, [&]() { return launch_linear_dgrad_simt(ctx, Y, W, X, dX, M, K, N, 0.01f); }, ms_out));
+        else
+            PPO_TRY(time_loop(ctx, sc, iters, flush_l2_flag, [&]() { return launch_linear_wgrad_simt(ctx, X, Y, dW, db, M, K, N, part, pb); }, ms_out));
+        *work_out = 2.0 * (double)M * K * N;
+        return PPO_OK;
+    }
+    set_error("bench_kernel: unknown kernel '%s'", which);
+    return PPO_ERR_INVALID;
+}

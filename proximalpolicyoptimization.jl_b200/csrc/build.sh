@@ -1,0 +1,25 @@
+#!/usr/bin/env bash
+# Build libppo_b200.so in-tree for sm_100a (B200).  Usage: csrc/build.sh [-j N]
+set -euo pipefail
+cd "$(dirname "$0")"
+OUT=../libppo_b200.so
+NVCC=${NVCC:-nvcc}
+FLAGS=(-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -Xcompiler -Wall
+       -Xptxas -v --expt-relaxed-constexpr)
+mkdir -p build
+pids=()
+for src in abi.cu scan.cu shuffle.cu gather.cu loss.cu gemm_simt.cu gemm_tc.cu adam.cu bench_hooks.cu; do
+  obj=build/${src%.cu}.o
+  if [[ ! -f $obj || $src -nt $obj || common.cuh -nt $obj || gemm_tc.cuh -nt $obj || ../../include/ppo_b200.h -nt $obj ]]; then
+    ( $NVCC "${FLAGS[@]}" -c "$src" -o "$obj" > "build/${src%.cu}.log" 2>&1 || { cat "build/${src%.cu}.log"; exit 1; } ) &
+    pids+=($!)
+  fi
+done
+obj=build/nccl_dl.o
+if [[ ! -f $obj || nccl_dl.cpp -nt $obj || common.cuh -nt $obj ]]; then
+  ( $NVCC "${FLAGS[@]}" -x cu -c nccl_dl.cpp -o $obj > build/nccl_dl.log 2>&1 || { cat build/nccl_dl.log; exit 1; } ) &
+  pids+=($!)
+fi
+for p in "${pids[@]:-}"; do [[ -n "$p" ]] && wait "$p"; done
+$NVCC -shared -o "$OUT" build/*.o -lcudart -lcuda -ldl
+echo "built $(realpath $OUT)"
