@@ -309,12 +309,12 @@ def run_ours(args):
             "gpu_launches": launches, "clocks": clocks,
             "loss_last_step": [float(last["loss"][0][0]), float(last["loss"][1][0])],
         }
+    if out is not None:
+        print(json.dumps(out), flush=True)
     barrier()
     pol.close(); buf.close(); ctx.close()
     if world > 1:
         dist.destroy_process_group()
-    if out is not None:
-        print(json.dumps(out), flush=True)
 
 
 def run_reference(args):

@@ -774,7 +774,7 @@ int ppo_adam_create(ppo_policy* p, double eta, double beta1, double beta2, doubl
     *out = nullptr;
     ppo_opt* o = new (std::nothrow) ppo_opt();
     if (!o) { set_error("out of host memory"); return PPO_ERR_NOMEM; }
-    o->policy = p; o->eta = eta; o->beta1 = beta1; o->beta2 = beta2; o->eps = eps;
+    o->ctx = ctx; o->policy = p; o->eta = eta; o->beta1 = beta1; o->beta2 = beta2; o->eps = eps;
     int s;
     if ((s = dev_alloc(&o->m, (size_t)p->P)) != PPO_OK || (s = dev_alloc(&o->v, (size_t)p->P)) != PPO_OK ||
         (s = dev_alloc(&o->d_bp, 2)) != PPO_OK) {
@@ -792,8 +792,8 @@ int ppo_adam_create(ppo_policy* p, double eta, double beta1, double beta2, doubl
 
 int ppo_adam_destroy(ppo_opt* o) {
     if (!o) return PPO_OK;
-    cudaSetDevice(o->policy->ctx->device);
-    cudaStreamSynchronize(o->policy->ctx->stream);
+    cudaSetDevice(o->ctx->device);
+    cudaStreamSynchronize(o->ctx->stream);
     dev_free(o->m); dev_free(o->v); dev_free(o->d_bp);
     delete o;
     return PPO_OK;

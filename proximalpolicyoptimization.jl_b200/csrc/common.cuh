@@ -125,6 +125,7 @@ struct ppo_policy {
 };
 
 struct ppo_opt {
+    ppo_ctx* ctx = nullptr;          // kept separately: the optimiser may outlive its policy handle
     ppo_policy* policy = nullptr;
     double eta = 1e-3, beta1 = 0.9, beta2 = 0.999, eps = 1e-8;
     float* m = nullptr;

@@ -9,6 +9,7 @@ device; ``weights()`` / ``load_weights()`` round-trip them as numpy arrays laid 
 from __future__ import annotations
 
 import ctypes as C
+import weakref
 
 import numpy as np
 
@@ -51,6 +52,7 @@ class Policy:
         _lib.check(_lib.load().ppo_policy_create(self.ctx.handle, L, dims, _pp(W), _pp(b), float(leaky_slope),
                                                  C.byref(h)))
         self._h = h
+        self._optimisers = weakref.WeakSet()
         self.ctx.adopt(self)
 
     @property
@@ -83,6 +85,8 @@ class Policy:
 
     def close(self):
         if self._h is not None:
+            for o in list(self._optimisers):     # optimiser state is keyed by this policy's parameters
+                o.close()
             _lib.load().ppo_policy_destroy(self._h)
             self._h = None
 
@@ -151,6 +155,7 @@ class Adam:
                                                    C.byref(h)))
             self._h, self._policy = h, policy
             policy.ctx.adopt(self)
+            policy._optimisers.add(self)
         elif self._policy is not policy:
             raise ValueError("this Adam instance already holds state for another policy")
         return self._h
@@ -166,6 +171,7 @@ class Adam:
         if self._h is not None:
             _lib.load().ppo_adam_destroy(self._h)
             self._h = None
+            self._policy = None
 
     def __del__(self):
         try:

@@ -3,7 +3,8 @@
 Tolerances:
   permutation, gather, permute!                 bit-exact
   returns, gamma == 1 and integer rewards        bit-exact
-  returns otherwise                              |d| <= 1e-6 + 1e-5 |x|  (Float64 carry on both sides)
+  returns otherwise                              |d| <= 1e-6 + 1e-5 |x|  (Float64 carry on both sides;
+                                                 2e-5 + 1e-5 |x| for a Float32 discount/carry)
   loss scalars                                   1e-5 relative
   dlogits given identical logits                 1e-5 relative + 1e-8 absolute
   weight gradients / post-Adam weights (fp32)    1e-5 relative of the tensor's max-abs (+1e-7)
@@ -51,8 +52,12 @@ def test_returns_discounted(ctx, gamma, p_term):
     r = rng.normal(size=n).astype(np.float32)
     t = rng.random(n) < p_term
     got = _scan(ctx, r, t, gamma)
-    want = CO.compute_returns(r, t, float(gamma), isinstance(gamma, np.float32))
-    assert np.all(np.abs(got - want) <= 1e-6 + 1e-5 * np.abs(want))
+    f32 = isinstance(gamma, np.float32)
+    want = CO.compute_returns(r, t, float(gamma), f32)
+    # Float64 carry (every in-tree call): 1e-6 abs + 1e-5 rel.  Float32 carry: the reference's own serial
+    # Float32 chain accumulates ~eps32*sqrt(horizon)*|v| of rounding, so the absolute part is 2e-5.
+    atol = 2e-5 if f32 else 1e-6
+    assert np.all(np.abs(got - want) <= atol + 1e-5 * np.abs(want))
 
 
 def test_returns_long_unterminated_and_single_step(ctx):
