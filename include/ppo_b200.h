@@ -191,6 +191,13 @@ int ppo_train(ppo_policy* p, ppo_opt* opt, ppo_buf* buf, double epsilon, int64_t
               int num_epochs, double entropy_weight, uint64_t seed, double* ppo_hist,
               double* entropy_hist, double* lr_hist);
 
+/* ---- one Dense-layer operation on host arrays through GEMM engine `mode` (tests, debugging) ----
+ * op 0 (Dense forward, test/policy.jl:11-15):   out[M,N] = act(X[M,K] W[K,N] + bias[N]); act = leakyrelu when slope >= 0
+ * op 1 (pullback w.r.t. the input + activation): out[M,K] = (dY[M,N] W[K,N]^T) .* leakyrelu'(X[M,K])
+ * op 2 (pullback w.r.t. weight and bias):        out[K,N] = X[M,K]^T dY[M,N];  out2[N] = colsum(dY) */
+int ppo_dense_op(ppo_ctx* ctx, int mode, int op, int64_t M, int K, int N, const float* X, const float* W,
+                 const float* bias, const float* dY, float slope, float* out, float* out2);
+
 /* ---- per-kernel timing hooks for bench.py (device pointers stay inside the library) ------- */
 /* run kernel `which` `iters` times on a synthetic device-resident problem and return the
  * average ms per launch measured with CUDA events on the ctx stream.  See bench.py. */

@@ -266,6 +266,7 @@ class Policy:
     def __init__(self, in_channels, hidden_channels, num_hidden_layers, num_output, rng=None, dtype=F32):
         dims = [in_channels] + [hidden_channels] * num_hidden_layers + [num_output]
         self.dims = dims
+        self.slope = LEAKY_SLOPE
         self.W, self.b = [], []
         rng = rng if rng is not None else np.random.default_rng(0)
         for i, o in zip(dims[:-1], dims[1:]):
@@ -280,6 +281,7 @@ class Policy:
     def copy(self):
         p = Policy.__new__(Policy)
         p.dims = list(self.dims)
+        p.slope = getattr(self, "slope", LEAKY_SLOPE)
         p.W = [w.copy() for w in self.W]
         p.b = [b.copy() for b in self.b]
         return p
@@ -302,7 +304,7 @@ def mlp_forward(policy: Policy, x, keep=False):
     L = len(policy.W)
     for l, (W, b) in enumerate(zip(policy.W, policy.b)):
         z = h @ W + b
-        h = leakyrelu(z) if l < L - 1 else z
+        h = leakyrelu(z, getattr(policy, "slope", LEAKY_SLOPE)) if l < L - 1 else z
         acts.append(h)
     return (h, acts) if keep else h
 
@@ -418,7 +420,7 @@ def policy_gradient(policy: Policy, feat, mask, actions1, old_probs, advantage, 
         if l > 0:
             dx = delta @ policy.W[l].T
             h = acts[l]
-            delta = np.where(h > 0, dx, dt.type(LEAKY_SLOPE) * dx)
+            delta = np.where(h > 0, dx, dt.type(getattr(policy, "slope", LEAKY_SLOPE)) * dx)
     return ppoloss, F64(entropyloss) * F64(entropy_weight), dW, db
 
 

@@ -69,6 +69,7 @@ SIGNATURES = {
     "ppo_step_batch": (c_int, [vp, vp, vp, c_i64, c_i64, c_dbl, c_dbl, PD, PD, PF]),
     "ppo_step_epoch": (c_int, [vp, vp, vp, c_dbl, c_i64, c_dbl, PD, PD]),
     "ppo_train": (c_int, [vp, vp, vp, c_dbl, c_i64, c_int, c_dbl, c_u64, PD, PD, PD]),
+    "ppo_dense_op": (c_int, [vp, c_int, c_int, c_i64, c_int, c_int, PF, PF, PF, PF, c_flt, PF, PF]),
     "ppo_bench_kernel": (c_int, [vp, C.c_char_p, c_i64, c_int, c_int, c_int, c_int, c_int, PD, PD]),
 }
 

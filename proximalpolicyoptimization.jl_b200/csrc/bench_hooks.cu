@@ -3,6 +3,7 @@
 // Used by bench.py for the per-kernel roofline numbers; not part of the reference-facing API.
 #include <string.h>
 
+#include <algorithm>
 #include <string>
 
 #include "common.cuh"
@@ -231,6 +232,84 @@ extern "C" int ppo_bench_kernel(ppo_ctx* ctx, const char* which, int64_t n, int 
         *work_out = 2.0 * (double)M * K * N;
         return PPO_OK;
     }
+    if (w == "tc1_fwd" || w == "tc1_dgrad" || w == "tc1_wgrad") {
+        const int64_t M = n; const int K = a, N = b;
+        tc_set_passes(c == 4 ? 4 : 3);
+        float *X, *Xl, *W, *Wl, *WT, *WTl, *bias, *Y, *Yl, *dX, *dXl, *dW, *part;
+        PPO_TRY(sc.alloc(&X, (size_t)M * K)); PPO_TRY(sc.alloc(&Xl, (size_t)M * K));
+        PPO_TRY(sc.alloc(&W, (size_t)K * N)); PPO_TRY(sc.alloc(&Wl, (size_t)K * N));
+        PPO_TRY(sc.alloc(&WT, (size_t)K * N)); PPO_TRY(sc.alloc(&WTl, (size_t)K * N)); PPO_TRY(sc.alloc(&bias, (size_t)N));
+        PPO_TRY(sc.alloc(&Y, (size_t)M * N)); PPO_TRY(sc.alloc(&Yl, (size_t)M * N));
+        PPO_TRY(sc.alloc(&dX, (size_t)M * K)); PPO_TRY(sc.alloc(&dXl, (size_t)M * K)); PPO_TRY(sc.alloc(&dW, (size_t)K * N));
+        const size_t pb = tc_test_wgrad_partial_bytes(ctx, M, K, N);
+        PPO_TRY(sc.alloc((char**)&part, pb));
+        PPO_TRY(fill(ctx, X, M * K, 0, 1, 1)); PPO_TRY(fill(ctx, W, (int64_t)K * N, 0, 1, 2));
+        PPO_TRY(fill(ctx, bias, N, 0, 1, 3)); PPO_TRY(fill(ctx, Y, M * N, 0, 1, 4));
+        PPO_TRY(tc_test_split_lo(ctx, X, Xl, M * K)); PPO_TRY(tc_test_split_lo(ctx, Y, Yl, M * N));
+        PPO_TRY(tc_test_weight_prep(ctx, W, Wl, WT, WTl, K, N));
+        if (w == "tc1_fwd")
+            PPO_TRY(time_loop(ctx, sc, iters, flush_l2_flag,
+                              [&]() { return tc_test_fwd(ctx, X, Xl, WT, WTl, bias, Y, Yl, M, K, N, 1, 0.01f); }, ms_out));
+        else if (w == "tc1_dgrad")
+            PPO_TRY(time_loop(ctx, sc, iters, flush_l2_flag,
+                              [&]() { return tc_test_dgrad(ctx, Y, Yl, W, Wl, X, dX, dXl, M, K, N, 0.01f); }, ms_out));
+        else
+            PPO_TRY(time_loop(ctx, sc, iters, flush_l2_flag,
+                              [&]() { return tc_test_wgrad(ctx, X, Xl, Y, Yl, dW, part, pb, M, K, N); }, ms_out));
+        *work_out = 2.0 * (double)M * K * N;
+        return PPO_OK;
+    }
     set_error("bench_kernel: unknown kernel '%s'", which);
     return PPO_ERR_INVALID;
+}
+
+extern "C" int ppo_dense_op(ppo_ctx* ctx, int mode, int op, int64_t M, int K, int N, const float* X, const float* W,
+                            const float* bias, const float* dY, float slope, float* out, float* out2) {
+    PPO_REQUIRE(ctx && X && W && out, "dense_op: null argument");
+    PPO_REQUIRE(op >= 0 && op <= 2 && M >= 1 && K >= 1 && N >= 1, "dense_op: bad op/shape");
+    PPO_REQUIRE(op == 0 || dY != nullptr, "dense_op: dY required");
+    PPO_REQUIRE(mode == PPO_GEMM_FP32_SIMT || mode == PPO_GEMM_TF32X3_TC, "dense_op: unsupported engine %d", mode);
+    PPO_CUDA(cudaSetDevice(ctx->device));
+    Scope sc;
+    float *dXp, *dWp, *dB, *dDY = nullptr, *dOut, *dOut2;
+    PPO_TRY(sc.alloc(&dXp, (size_t)M * K)); PPO_TRY(sc.alloc(&dWp, (size_t)K * N)); PPO_TRY(sc.alloc(&dB, (size_t)N));
+    PPO_TRY(sc.alloc(&dOut2, (size_t)N));
+    const size_t out_elems = op == 0 ? (size_t)M * N : (op == 1 ? (size_t)M * K : (size_t)K * N);
+    PPO_TRY(sc.alloc(&dOut, out_elems));
+    cudaStream_t s = ctx->stream;
+    PPO_CUDA(cudaMemcpyAsync(dXp, X, (size_t)M * K * 4, cudaMemcpyHostToDevice, s));
+    PPO_CUDA(cudaMemcpyAsync(dWp, W, (size_t)K * N * 4, cudaMemcpyHostToDevice, s));
+    if (bias) PPO_CUDA(cudaMemcpyAsync(dB, bias, (size_t)N * 4, cudaMemcpyHostToDevice, s));
+    else PPO_CUDA(cudaMemsetAsync(dB, 0, (size_t)N * 4, s));
+    if (dY) {
+        PPO_TRY(sc.alloc(&dDY, (size_t)M * N));
+        PPO_CUDA(cudaMemcpyAsync(dDY, dY, (size_t)M * N * 4, cudaMemcpyHostToDevice, s));
+    }
+    const bool act = slope >= 0.0f;
+    if (mode == PPO_GEMM_FP32_SIMT) {
+        float* part; const size_t pb = wgrad_partial_bytes(M, K, N);
+        PPO_TRY(sc.alloc((char**)&part, pb));
+        if (op == 0) PPO_TRY(launch_linear_fwd_simt(ctx, dXp, dWp, dB, dOut, M, K, N, act, slope));
+        else if (op == 1) PPO_TRY(launch_linear_dgrad_simt(ctx, dDY, dWp, dXp, dOut, M, K, N, slope));
+        else PPO_TRY(launch_linear_wgrad_simt(ctx, dXp, dDY, dOut, dOut2, M, K, N, part, pb));
+    } else {
+        float *Xl, *Wl, *WT, *WTl, *DYl = nullptr, *Ol, *part;
+        PPO_TRY(sc.alloc(&Xl, (size_t)M * K)); PPO_TRY(sc.alloc(&Wl, (size_t)K * N)); PPO_TRY(sc.alloc(&WT, (size_t)K * N));
+        PPO_TRY(sc.alloc(&WTl, (size_t)K * N)); PPO_TRY(sc.alloc(&Ol, out_elems));
+        PPO_TRY(tc_test_split_lo(ctx, dXp, Xl, M * K));
+        PPO_TRY(tc_test_weight_prep(ctx, dWp, Wl, WT, WTl, K, N));
+        if (dDY) { PPO_TRY(sc.alloc(&DYl, (size_t)M * N)); PPO_TRY(tc_test_split_lo(ctx, dDY, DYl, M * N)); }
+        if (op == 0) PPO_TRY(tc_test_fwd(ctx, dXp, Xl, WT, WTl, dB, dOut, Ol, M, K, N, act ? 1 : 0, slope));
+        else if (op == 1) PPO_TRY(tc_test_dgrad(ctx, dDY, DYl, dWp, Wl, dXp, dOut, Ol, M, K, N, slope));
+        else {
+            const size_t pb = std::max(tc_test_wgrad_partial_bytes(ctx, M, K, N), (size_t)ctx->num_sms * 4 * N * 4);
+            PPO_TRY(sc.alloc((char**)&part, pb));
+            PPO_TRY(tc_test_wgrad(ctx, dXp, Xl, dDY, DYl, dOut, part, pb, M, K, N));
+            PPO_TRY(tc_test_colsum(ctx, dDY, M, N, part, dOut2));
+        }
+    }
+    PPO_CUDA(cudaMemcpyAsync(out, dOut, out_elems * 4, cudaMemcpyDeviceToHost, s));
+    if (op == 2 && out2) PPO_CUDA(cudaMemcpyAsync(out2, dOut2, (size_t)N * 4, cudaMemcpyDeviceToHost, s));
+    PPO_CUDA(cudaStreamSynchronize(s));
+    return PPO_OK;
 }
