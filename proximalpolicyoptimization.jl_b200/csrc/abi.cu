@@ -154,7 +154,8 @@ int policy_forward(ppo_policy* p, const float* X, int64_t M) {
         const float* b = p->params + p->b_off[l];
         const bool last = (l == L - 1);
         if (last) {
-            PPO_TRY(launch_head_fwd(ctx, in, W, b, p->act[l + 1], M, K, N));
+            const float* in_lo = (p->gemm_mode != PPO_GEMM_FP32_SIMT && l > 0) ? tc_act_lo(p, l) : nullptr;
+            PPO_TRY(launch_head_fwd(ctx, in, in_lo, W, b, p->act[l + 1], M, K, N));
         } else if (p->gemm_mode == PPO_GEMM_FP32_SIMT) {
             PPO_TRY(launch_linear_fwd_simt(ctx, in, W, b, p->act[l + 1], M, K, N, true, p->slope));
         } else {
@@ -179,8 +180,9 @@ int policy_backward(ppo_policy* p, const float* X, int64_t M) {
         const float* in = (l == 0) ? X : p->act[l];
         float* dX = (l == 0) ? nullptr : p->dact[pp];
         if (l == L - 1) {
-            PPO_TRY(launch_head_bwd(ctx, in, delta, W, dX, dW, db, M, K, N, p->slope, p->partial, p->partial_bytes,
-                                    l > 0));
+            const float* in_lo = (p->gemm_mode != PPO_GEMM_FP32_SIMT && l > 0) ? tc_act_lo(p, l) : nullptr;
+            PPO_TRY(launch_head_bwd(ctx, in, in_lo, delta, W, dX, dW, db, M, K, N, p->slope, p->partial,
+                                    p->partial_bytes, l > 0));
         } else if (p->gemm_mode == PPO_GEMM_FP32_SIMT) {
             PPO_TRY(launch_linear_wgrad_simt(ctx, in, delta, dW, db, M, K, N, p->partial, p->partial_bytes));
             if (l > 0) PPO_TRY(launch_linear_dgrad_simt(ctx, delta, W, in, dX, M, K, N, p->slope));

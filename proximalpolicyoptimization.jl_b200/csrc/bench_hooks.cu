@@ -43,6 +43,15 @@ __global__ void fill_zero_i32_kernel(int* p, int64_t n) {
         p[i] = 0;
 }
 
+__global__ void axpy_kernel(float* y, const float* x, int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) y[i] += x[i];
+}
+int launch_axpy(ppo_ctx* ctx, float* y, const float* x, int64_t n) {
+    axpy_kernel<<<(unsigned)std::min<int64_t>(ceil_div(n, 256), 148 * 16), 256, 0, ctx->stream>>>(y, x, n);
+    PPO_CUDA(cudaGetLastError());
+    return PPO_OK;
+}
+
 struct Scope {  // frees everything on exit
     std::vector<void*> ptrs;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
@@ -203,11 +212,11 @@ extern "C" int ppo_bench_kernel(ppo_ctx* ctx, const char* which, int64_t n, int 
         PPO_TRY(fill(ctx, H, M * K, 0, 1, 1)); PPO_TRY(fill(ctx, W, (int64_t)K * N, 0, 1, 2));
         PPO_TRY(fill(ctx, bias, N, 0, 1, 3)); PPO_TRY(fill(ctx, lg, M * N, 0, 1, 4));
         if (w == "head_fwd") {
-            PPO_TRY(time_loop(ctx, sc, iters, flush_l2_flag, [&]() { return launch_head_fwd(ctx, H, W, bias, lg, M, K, N); }, ms_out));
+            PPO_TRY(time_loop(ctx, sc, iters, flush_l2_flag, [&]() { return launch_head_fwd(ctx, H, nullptr, W, bias, lg, M, K, N); }, ms_out));
             *work_out = (double)M * (4.0 * K + 4.0 * N);
         } else {
             PPO_TRY(time_loop(ctx, sc, iters, flush_l2_flag,
-                              [&]() { return launch_head_bwd(ctx, H, lg, W, dH, dW, db, M, K, N, 0.01f, part, pb, true); }, ms_out));
+                              [&]() { return launch_head_bwd(ctx, H, nullptr, lg, W, dH, dW, db, M, K, N, 0.01f, part, pb, true); }, ms_out));
             *work_out = (double)M * (8.0 * K + 4.0 * N);
         }
         return PPO_OK;
@@ -234,28 +243,28 @@ extern "C" int ppo_bench_kernel(ppo_ctx* ctx, const char* which, int64_t n, int 
     }
     if (w == "tc1_fwd" || w == "tc1_dgrad" || w == "tc1_wgrad") {
         const int64_t M = n; const int K = a, N = b;
-        tc_set_passes(c == 4 ? 4 : 3);
-        float *X, *Xl, *W, *Wl, *WT, *WTl, *bias, *Y, *Yl, *dX, *dXl, *dW, *part;
-        PPO_TRY(sc.alloc(&X, (size_t)M * K)); PPO_TRY(sc.alloc(&Xl, (size_t)M * K));
-        PPO_TRY(sc.alloc(&W, (size_t)K * N)); PPO_TRY(sc.alloc(&Wl, (size_t)K * N));
-        PPO_TRY(sc.alloc(&WT, (size_t)K * N)); PPO_TRY(sc.alloc(&WTl, (size_t)K * N)); PPO_TRY(sc.alloc(&bias, (size_t)N));
+        float *X, *Xl, *W, *Wh, *Wl, *WTh, *WTl, *bias, *Y, *Yl, *dX, *dXl, *dW, *db, *part;
+        PPO_TRY(sc.alloc(&X, (size_t)M * K + 64)); PPO_TRY(sc.alloc(&Xl, (size_t)M * K + 64));
+        PPO_TRY(sc.alloc(&W, (size_t)K * N)); PPO_TRY(sc.alloc(&Wh, (size_t)K * N)); PPO_TRY(sc.alloc(&Wl, (size_t)K * N));
+        PPO_TRY(sc.alloc(&WTh, (size_t)K * N)); PPO_TRY(sc.alloc(&WTl, (size_t)K * N)); PPO_TRY(sc.alloc(&bias, (size_t)N));
         PPO_TRY(sc.alloc(&Y, (size_t)M * N)); PPO_TRY(sc.alloc(&Yl, (size_t)M * N));
         PPO_TRY(sc.alloc(&dX, (size_t)M * K)); PPO_TRY(sc.alloc(&dXl, (size_t)M * K)); PPO_TRY(sc.alloc(&dW, (size_t)K * N));
-        const size_t pb = tc_test_wgrad_partial_bytes(ctx, M, K, N);
+        PPO_TRY(sc.alloc(&db, (size_t)N));
+        const size_t pb = tc_test_partial_bytes(ctx, M, K, N);
         PPO_TRY(sc.alloc((char**)&part, pb));
         PPO_TRY(fill(ctx, X, M * K, 0, 1, 1)); PPO_TRY(fill(ctx, W, (int64_t)K * N, 0, 1, 2));
         PPO_TRY(fill(ctx, bias, N, 0, 1, 3)); PPO_TRY(fill(ctx, Y, M * N, 0, 1, 4));
-        PPO_TRY(tc_test_split_lo(ctx, X, Xl, M * K)); PPO_TRY(tc_test_split_lo(ctx, Y, Yl, M * N));
-        PPO_TRY(tc_test_weight_prep(ctx, W, Wl, WT, WTl, K, N));
+        PPO_TRY(tc_test_split(ctx, X, X, Xl, M * K)); PPO_TRY(tc_test_split(ctx, Y, Y, Yl, M * N));
+        PPO_TRY(tc_test_weight_prep(ctx, W, Wh, Wl, WTh, WTl, K, N));
         if (w == "tc1_fwd")
             PPO_TRY(time_loop(ctx, sc, iters, flush_l2_flag,
-                              [&]() { return tc_test_fwd(ctx, X, Xl, WT, WTl, bias, Y, Yl, M, K, N, 1, 0.01f); }, ms_out));
+                              [&]() { return tc_test_fwd(ctx, X, Xl, WTh, WTl, bias, Y, Yl, M, K, N, 1, 0.01f); }, ms_out));
         else if (w == "tc1_dgrad")
             PPO_TRY(time_loop(ctx, sc, iters, flush_l2_flag,
-                              [&]() { return tc_test_dgrad(ctx, Y, Yl, W, Wl, X, dX, dXl, M, K, N, 0.01f); }, ms_out));
+                              [&]() { return tc_test_dgrad(ctx, Y, Yl, Wh, Wl, X, dX, dXl, M, K, N, 0.01f); }, ms_out));
         else
             PPO_TRY(time_loop(ctx, sc, iters, flush_l2_flag,
-                              [&]() { return tc_test_wgrad(ctx, X, Xl, Y, Yl, dW, part, pb, M, K, N); }, ms_out));
+                              [&]() { return tc_test_wgrad(ctx, X, Xl, Y, Yl, dW, db, part, pb, M, K, N); }, ms_out));
         *work_out = 2.0 * (double)M * K * N;
         return PPO_OK;
     }
@@ -293,19 +302,27 @@ extern "C" int ppo_dense_op(ppo_ctx* ctx, int mode, int op, int64_t M, int K, in
         else if (op == 1) PPO_TRY(launch_linear_dgrad_simt(ctx, dDY, dWp, dXp, dOut, M, K, N, slope));
         else PPO_TRY(launch_linear_wgrad_simt(ctx, dXp, dDY, dOut, dOut2, M, K, N, part, pb));
     } else {
-        float *Xl, *Wl, *WT, *WTl, *DYl = nullptr, *Ol, *part;
-        PPO_TRY(sc.alloc(&Xl, (size_t)M * K)); PPO_TRY(sc.alloc(&Wl, (size_t)K * N)); PPO_TRY(sc.alloc(&WT, (size_t)K * N));
-        PPO_TRY(sc.alloc(&WTl, (size_t)K * N)); PPO_TRY(sc.alloc(&Ol, out_elems));
-        PPO_TRY(tc_test_split_lo(ctx, dXp, Xl, M * K));
-        PPO_TRY(tc_test_weight_prep(ctx, dWp, Wl, WT, WTl, K, N));
-        if (dDY) { PPO_TRY(sc.alloc(&DYl, (size_t)M * N)); PPO_TRY(tc_test_split_lo(ctx, dDY, DYl, M * N)); }
-        if (op == 0) PPO_TRY(tc_test_fwd(ctx, dXp, Xl, WT, WTl, dB, dOut, Ol, M, K, N, act ? 1 : 0, slope));
-        else if (op == 1) PPO_TRY(tc_test_dgrad(ctx, dDY, DYl, dWp, Wl, dXp, dOut, Ol, M, K, N, slope));
-        else {
-            const size_t pb = std::max(tc_test_wgrad_partial_bytes(ctx, M, K, N), (size_t)ctx->num_sms * 4 * N * 4);
+        // tensor-core engine: operands as tf32 hi/lo pairs; the result is hi + lo of the output pair
+        float *Xh, *Xl, *Wh, *Wl, *WTh, *WTl, *DYh = nullptr, *DYl = nullptr, *Ol, *part;
+        PPO_TRY(sc.alloc(&Xh, (size_t)M * K + 64)); PPO_TRY(sc.alloc(&Xl, (size_t)M * K + 64));
+        PPO_TRY(sc.alloc(&Wh, (size_t)K * N)); PPO_TRY(sc.alloc(&Wl, (size_t)K * N));
+        PPO_TRY(sc.alloc(&WTh, (size_t)K * N)); PPO_TRY(sc.alloc(&WTl, (size_t)K * N)); PPO_TRY(sc.alloc(&Ol, out_elems));
+        PPO_TRY(tc_test_split(ctx, dXp, Xh, Xl, M * K));
+        PPO_TRY(tc_test_weight_prep(ctx, dWp, Wh, Wl, WTh, WTl, K, N));
+        if (dDY) {
+            PPO_TRY(sc.alloc(&DYh, (size_t)M * N)); PPO_TRY(sc.alloc(&DYl, (size_t)M * N));
+            PPO_TRY(tc_test_split(ctx, dDY, DYh, DYl, M * N));
+        }
+        if (op == 0) {
+            PPO_TRY(tc_test_fwd(ctx, Xh, Xl, WTh, WTl, dB, dOut, Ol, M, K, N, act ? 1 : 0, slope));
+            PPO_TRY(launch_axpy(ctx, dOut, Ol, (int64_t)out_elems));
+        } else if (op == 1) {
+            PPO_TRY(tc_test_dgrad(ctx, DYh, DYl, Wh, Wl, dXp, dOut, Ol, M, K, N, slope));
+            PPO_TRY(launch_axpy(ctx, dOut, Ol, (int64_t)out_elems));
+        } else {
+            const size_t pb = tc_test_partial_bytes(ctx, M, K, N);
             PPO_TRY(sc.alloc((char**)&part, pb));
-            PPO_TRY(tc_test_wgrad(ctx, dXp, Xl, dDY, DYl, dOut, part, pb, M, K, N));
-            PPO_TRY(tc_test_colsum(ctx, dDY, M, N, part, dOut2));
+            PPO_TRY(tc_test_wgrad(ctx, Xh, Xl, DYh, DYl, dOut, dOut2, part, pb, M, K, N));
         }
     }
     PPO_CUDA(cudaMemcpyAsync(out, dOut, out_elems * 4, cudaMemcpyDeviceToHost, s));

@@ -185,10 +185,11 @@ int launch_linear_dgrad_simt(ppo_ctx* ctx, const float* dY, const float* W, cons
 int launch_linear_wgrad_simt(ppo_ctx* ctx, const float* X, const float* dY, float* dW, float* db,
                              int64_t M, int K, int N, float* partial, size_t partial_bytes);
 size_t wgrad_partial_bytes(int64_t M, int K, int N);
-int launch_head_fwd(ppo_ctx* ctx, const float* H, const float* W, const float* bias, float* logits,
-                    int64_t M, int K, int N);
-int launch_head_bwd(ppo_ctx* ctx, const float* H, const float* dlogits, const float* W, float* dH,
-                    float* dW, float* db, int64_t M, int K, int N, float slope, float* partial,
+// Hlo: optional lo companion of H (tensor-core mode keeps activations as tf32 hi + lo pairs)
+int launch_head_fwd(ppo_ctx* ctx, const float* H, const float* Hlo, const float* W, const float* bias,
+                    float* logits, int64_t M, int K, int N);
+int launch_head_bwd(ppo_ctx* ctx, const float* H, const float* Hlo, const float* dlogits, const float* W,
+                    float* dH, float* dW, float* db, int64_t M, int K, int N, float slope, float* partial,
                     size_t partial_bytes, bool need_dH);
 
 // adam.cu (K8)

@@ -225,8 +225,8 @@ constexpr int HEAD_NMAX = 8;
 
 template <int N>
 __global__ void __launch_bounds__(256)
-head_fwd_kernel(const float* __restrict__ H, const float* __restrict__ W, const float* __restrict__ bias,
-                float* __restrict__ logits, int64_t M, int K) {
+head_fwd_kernel(const float* __restrict__ H, const float* __restrict__ Hlo, const float* __restrict__ W,
+                const float* __restrict__ bias, float* __restrict__ logits, int64_t M, int K) {
     extern __shared__ __align__(16) float sW[];   // [K][N]
     for (int i = threadIdx.x; i < K * N; i += blockDim.x) sW[i] = W[i];
     __syncthreads();
@@ -234,11 +234,13 @@ head_fwd_kernel(const float* __restrict__ H, const float* __restrict__ W, const 
     const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     for (int64_t m = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; m < M; m += warps) {
         const float4* hp = reinterpret_cast<const float4*>(H + m * K);
+        const float4* lp = Hlo ? reinterpret_cast<const float4*>(Hlo + m * K) : nullptr;
         float acc[N];
 #pragma unroll
         for (int n = 0; n < N; ++n) acc[n] = 0.0f;
         for (int kv = lane; kv < (K >> 2); kv += 32) {
-            const float4 h = hp[kv];
+            float4 h = hp[kv];
+            if (lp) { const float4 l = lp[kv]; h.x += l.x; h.y += l.y; h.z += l.z; h.w += l.w; }   // exact = hi + lo
             const float hv[4] = {h.x, h.y, h.z, h.w};
 #pragma unroll
             for (int c = 0; c < 4; ++c)
@@ -259,7 +261,8 @@ head_fwd_kernel(const float* __restrict__ H, const float* __restrict__ W, const 
 // one pass over H: dH = (dlogits W^T) .* leakyrelu'(H); per-CTA partial dW[k][n], db[n]
 template <int N, int KPT>   // KPT = ceil(K / 256) columns per thread
 __global__ void __launch_bounds__(256)
-head_bwd_kernel(const float* __restrict__ H, const float* __restrict__ dlogits, const float* __restrict__ W,
+head_bwd_kernel(const float* __restrict__ H, const float* __restrict__ Hlo, const float* __restrict__ dlogits,
+                const float* __restrict__ W,
                 float* __restrict__ dH, float* __restrict__ partial, int64_t M, int K, float slope,
                 int64_t rows_per_cta, int need_dH) {
     const int tid = threadIdx.x;
@@ -285,7 +288,7 @@ head_bwd_kernel(const float* __restrict__ H, const float* __restrict__ dlogits, 
 #pragma unroll
             for (int q = 0; q < KPT; ++q) {
                 const int k = tid + q * 256;
-                h[u][q] = (rv && k < K) ? H[(m + u) * K + k] : 0.0f;
+                h[u][q] = (rv && k < K) ? (H[(m + u) * K + k] + (Hlo ? Hlo[(m + u) * K + k] : 0.0f)) : 0.0f;
             }
 #pragma unroll
             for (int n = 0; n < N; ++n) d[u][n] = rv ? __ldg(dlogits + (m + u) * N + n) : 0.0f;
@@ -395,16 +398,18 @@ int launch_linear_wgrad_simt(ppo_ctx* ctx, const float* X, const float* dY, floa
     return PPO_OK;
 }
 
-int launch_head_fwd(ppo_ctx* ctx, const float* H, const float* W, const float* bias, float* logits, int64_t M,
-                    int K, int N) {
-    if (N > HEAD_NMAX || (K & 3) != 0 || (size_t)K * N * 4 > 48 * 1024 || ((uintptr_t)H & 15) != 0)
+int launch_head_fwd(ppo_ctx* ctx, const float* H, const float* Hlo, const float* W, const float* bias, float* logits,
+                    int64_t M, int K, int N) {
+    if (N > HEAD_NMAX || (K & 3) != 0 || (size_t)K * N * 4 > 48 * 1024 || ((uintptr_t)H & 15) != 0) {
+        PPO_REQUIRE(Hlo == nullptr, "head_fwd: hi/lo activations need N <= %d and K %% 4 == 0", HEAD_NMAX);
         return launch_linear_fwd_simt(ctx, H, W, bias, logits, M, K, N, false, 0.0f);
+    }
     int64_t blocks = ceil_div(M, 8);
     const int64_t cap = (int64_t)ctx->num_sms * 8;
     if (blocks > cap) blocks = cap;
     const size_t smem = (size_t)K * N * sizeof(float);
 #define PPO_HEAD_FWD(N_) \
-    case N_: head_fwd_kernel<N_><<<(unsigned)blocks, 256, smem, ctx->stream>>>(H, W, bias, logits, M, K); break
+    case N_: head_fwd_kernel<N_><<<(unsigned)blocks, 256, smem, ctx->stream>>>(H, Hlo, W, bias, logits, M, K); break
     switch (N) {
         PPO_HEAD_FWD(1); PPO_HEAD_FWD(2); PPO_HEAD_FWD(3); PPO_HEAD_FWD(4);
         PPO_HEAD_FWD(5); PPO_HEAD_FWD(6); PPO_HEAD_FWD(7); PPO_HEAD_FWD(8);
@@ -415,10 +420,11 @@ int launch_head_fwd(ppo_ctx* ctx, const float* H, const float* W, const float* b
     return PPO_OK;
 }
 
-int launch_head_bwd(ppo_ctx* ctx, const float* H, const float* dlogits, const float* W, float* dH, float* dW,
-                    float* db, int64_t M, int K, int N, float slope, float* partial, size_t partial_bytes,
+int launch_head_bwd(ppo_ctx* ctx, const float* H, const float* Hlo, const float* dlogits, const float* W, float* dH,
+                    float* dW, float* db, int64_t M, int K, int N, float slope, float* partial, size_t partial_bytes,
                     bool need_dH) {
     if (N > 4 || K > 1024) {
+        PPO_REQUIRE(Hlo == nullptr, "head_bwd: hi/lo activations need N <= 4 and K <= 1024");
         // generic path through the tile GEMMs
         if (need_dH) PPO_TRY(launch_linear_dgrad_simt(ctx, dlogits, W, H, dH, M, K, N, slope));
         return launch_linear_wgrad_simt(ctx, H, dlogits, dW, db, M, K, N, partial, partial_bytes);
@@ -430,7 +436,7 @@ int launch_head_bwd(ppo_ctx* ctx, const float* H, const float* dlogits, const fl
     const int kpt = (int)ceil_div(K, 256);
 #define PPO_HEAD_BWD(N_, Q_)                                                                          \
     if (N == N_ && kpt == Q_)                                                                          \
-        head_bwd_kernel<N_, Q_><<<(unsigned)ctas, 256, 0, ctx->stream>>>(H, dlogits, W, dH, partial, M, K, \
+        head_bwd_kernel<N_, Q_><<<(unsigned)ctas, 256, 0, ctx->stream>>>(H, Hlo, dlogits, W, dH, partial, M, K, \
                                                                          slope, rows, need_dH ? 1 : 0)
     PPO_HEAD_BWD(1, 1); PPO_HEAD_BWD(1, 2); PPO_HEAD_BWD(1, 3); PPO_HEAD_BWD(1, 4);
     PPO_HEAD_BWD(2, 1); PPO_HEAD_BWD(2, 2); PPO_HEAD_BWD(2, 3); PPO_HEAD_BWD(2, 4);

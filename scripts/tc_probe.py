@@ -58,7 +58,7 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "time":
         import ppo_b200 as P
         ctx = P.Context(0)
-        for which, c in (("tc1_fwd", 3), ("tc1_fwd", 4), ("tc1_dgrad", 3), ("tc1_dgrad", 4), ("tc1_wgrad", 3), ("gemm_fwd", 0)):
+        for which, c in (("tc1_fwd", 3), ("tc1_dgrad", 3), ("tc1_wgrad", 3)):
             ms, fl = ctx.bench_kernel(which, 1 << 20, 512, 512, c, 3, True)
             print(f"{which} passes={c}: {ms:.3f} ms, {fl / ms / 1e9:.1f} TFLOP/s (fp32-equivalent)", flush=True)
         for which, c in (("tc1_fwd", 3), ("tc1_wgrad", 3)):
@@ -66,7 +66,8 @@ if __name__ == "__main__":
             print(f"{which} K=64 passes={c}: {ms:.3f} ms, {fl / ms / 1e9:.1f} TFLOP/s", flush=True)
         sys.exit(0)
     cases = [
-        (1, 2, 4096, 512, 512), (1, 2, 100000, 512, 512), (1, 2, 1000000, 64, 512), (0, 2, 100000, 512, 512),
+        (1, 0, 1000, 512, 512), (1, 0, 65536, 512, 512), (1, 0, 300, 72, 128), (1, 1, 1000, 512, 512),
+        (1, 2, 4096, 512, 512), (1, 2, 100000, 512, 512), (1, 2, 1000000, 64, 512), (1, 2, 1000, 72, 128),
     ]
     for c in cases:
         try:
