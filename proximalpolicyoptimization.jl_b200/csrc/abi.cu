@@ -170,6 +170,7 @@ int policy_forward(ppo_policy* p, const float* X, int64_t M) {
 int policy_backward(ppo_policy* p, const float* X, int64_t M) {
     ppo_ctx* ctx = p->ctx;
     const int L = p->L;
+    const bool tc = p->gemm_mode != PPO_GEMM_FP32_SIMT;
     const float* delta = p->dlogits;
     int pp = 0;
     for (int l = L - 1; l >= 0; --l) {
@@ -177,17 +178,21 @@ int policy_backward(ppo_policy* p, const float* X, int64_t M) {
         const float* W = p->params + p->w_off[l];
         float* dW = p->grads + p->w_off[l];
         float* db = p->grads + p->b_off[l];
+        float* db_below = (l > 0) ? p->grads + p->b_off[l - 1] : nullptr;
         const float* in = (l == 0) ? X : p->act[l];
         float* dX = (l == 0) ? nullptr : p->dact[pp];
         if (l == L - 1) {
-            const float* in_lo = (p->gemm_mode != PPO_GEMM_FP32_SIMT && l > 0) ? tc_act_lo(p, l) : nullptr;
-            PPO_TRY(launch_head_bwd(ctx, in, in_lo, delta, W, dX, dW, db, M, K, N, p->slope, p->partial,
-                                    p->partial_bytes, l > 0));
-        } else if (p->gemm_mode == PPO_GEMM_FP32_SIMT) {
+            // the head: in tensor-core mode it reads the hi/lo activation pair, writes dX as a hi/lo pair and
+            // emits the bias gradient of the layer below (colsum of dX) in the same pass
+            const float* in_lo = (tc && l > 0) ? tc_act_lo(p, l) : nullptr;
+            float* dX_lo = (tc && dX != nullptr) ? tc_dact_lo(p, dX) : nullptr;
+            PPO_TRY(launch_head_bwd(ctx, in, in_lo, delta, W, dX, dX_lo, dW, db, tc ? db_below : nullptr, M, K, N,
+                                    p->slope, p->partial, p->partial_bytes, l > 0));
+        } else if (!tc) {
             PPO_TRY(launch_linear_wgrad_simt(ctx, in, delta, dW, db, M, K, N, p->partial, p->partial_bytes));
             if (l > 0) PPO_TRY(launch_linear_dgrad_simt(ctx, delta, W, in, dX, M, K, N, p->slope));
         } else {
-            PPO_TRY(tc_linear_bwd(p, l, in, delta, dX, dW, db, M));
+            PPO_TRY(tc_linear_bwd(p, l, in, delta, dX, dW, db_below, M));
         }
         delta = dX;
         pp ^= 1;

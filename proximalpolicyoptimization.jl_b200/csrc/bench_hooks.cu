@@ -216,7 +216,7 @@ extern "C" int ppo_bench_kernel(ppo_ctx* ctx, const char* which, int64_t n, int 
             *work_out = (double)M * (4.0 * K + 4.0 * N);
         } else {
             PPO_TRY(time_loop(ctx, sc, iters, flush_l2_flag,
-                              [&]() { return launch_head_bwd(ctx, H, nullptr, lg, W, dH, dW, db, M, K, N, 0.01f, part, pb, true); }, ms_out));
+                              [&]() { return launch_head_bwd(ctx, H, nullptr, lg, W, dH, nullptr, dW, db, nullptr, M, K, N, 0.01f, part, pb, true); }, ms_out));
             *work_out = (double)M * (8.0 * K + 4.0 * N);
         }
         return PPO_OK;
@@ -261,7 +261,7 @@ extern "C" int ppo_bench_kernel(ppo_ctx* ctx, const char* which, int64_t n, int 
                               [&]() { return tc_test_fwd(ctx, X, Xl, WTh, WTl, bias, Y, Yl, M, K, N, 1, 0.01f); }, ms_out));
         else if (w == "tc1_dgrad")
             PPO_TRY(time_loop(ctx, sc, iters, flush_l2_flag,
-                              [&]() { return tc_test_dgrad(ctx, Y, Yl, Wh, Wl, X, dX, dXl, M, K, N, 0.01f); }, ms_out));
+                              [&]() { return tc_test_dgrad(ctx, Y, Yl, Wh, Wl, X, dX, dXl, M, K, N, 0.01f, part, db); }, ms_out));
         else
             PPO_TRY(time_loop(ctx, sc, iters, flush_l2_flag,
                               [&]() { return tc_test_wgrad(ctx, X, Xl, Y, Yl, dW, db, part, pb, M, K, N); }, ms_out));
@@ -317,8 +317,12 @@ extern "C" int ppo_dense_op(ppo_ctx* ctx, int mode, int op, int64_t M, int K, in
             PPO_TRY(tc_test_fwd(ctx, Xh, Xl, WTh, WTl, dB, dOut, Ol, M, K, N, act ? 1 : 0, slope));
             PPO_TRY(launch_axpy(ctx, dOut, Ol, (int64_t)out_elems));
         } else if (op == 1) {
-            PPO_TRY(tc_test_dgrad(ctx, DYh, DYl, Wh, Wl, dXp, dOut, Ol, M, K, N, slope));
+            float *cs_scratch, *cs_out;
+            PPO_TRY(sc.alloc((char**)&cs_scratch, tc_test_partial_bytes(ctx, M, K, N)));
+            PPO_TRY(sc.alloc(&cs_out, (size_t)K));
+            PPO_TRY(tc_test_dgrad(ctx, DYh, DYl, Wh, Wl, dXp, dOut, Ol, M, K, N, slope, cs_scratch, cs_out));
             PPO_TRY(launch_axpy(ctx, dOut, Ol, (int64_t)out_elems));
+            if (out2) PPO_CUDA(cudaMemcpyAsync(out2, cs_out, (size_t)K * 4, cudaMemcpyDeviceToHost, s));
         } else {
             const size_t pb = tc_test_partial_bytes(ctx, M, K, N);
             PPO_TRY(sc.alloc((char**)&part, pb));

@@ -188,9 +188,10 @@ size_t wgrad_partial_bytes(int64_t M, int K, int N);
 // Hlo: optional lo companion of H (tensor-core mode keeps activations as tf32 hi + lo pairs)
 int launch_head_fwd(ppo_ctx* ctx, const float* H, const float* Hlo, const float* W, const float* bias,
                     float* logits, int64_t M, int K, int N);
+// dHlo: write dH as a tf32 hi/lo pair; db_below: also emit colsum(dH) = bias gradient of the layer below
 int launch_head_bwd(ppo_ctx* ctx, const float* H, const float* Hlo, const float* dlogits, const float* W,
-                    float* dH, float* dW, float* db, int64_t M, int K, int N, float slope, float* partial,
-                    size_t partial_bytes, bool need_dH);
+                    float* dH, float* dHlo, float* dW, float* db, float* db_below, int64_t M, int K, int N,
+                    float slope, float* partial, size_t partial_bytes, bool need_dH);
 
 // adam.cu (K8)
 int launch_adam(ppo_ctx* ctx, float* x, float* m, float* v, const float* g, int64_t n, double eta,

@@ -223,58 +223,96 @@ reduce_partials_kernel(const float* __restrict__ partial, int64_t splits, int64_
 // ---- policy head: N = apa <= 8 -----------------------------------------------------------
 constexpr int HEAD_NMAX = 8;
 
-template <int N>
+// logits[m][n] = sum_k (H[m][k] (+ Hlo[m][k])) W[k][n] + b[n]: one warp per token row, two rows in flight.
+// W is staged in shared memory as [c][n][k/4] so that the 32 lanes (consecutive k/4) read consecutive words.
+template <int N, bool HAS_LO>
 __global__ void __launch_bounds__(256)
 head_fwd_kernel(const float* __restrict__ H, const float* __restrict__ Hlo, const float* __restrict__ W,
                 const float* __restrict__ bias, float* __restrict__ logits, int64_t M, int K) {
-    extern __shared__ __align__(16) float sW[];   // [K][N]
-    for (int i = threadIdx.x; i < K * N; i += blockDim.x) sW[i] = W[i];
+    extern __shared__ __align__(16) float sW[];   // [4][N][K/4]
+    const int KV = K >> 2;
+    for (int i = threadIdx.x; i < K * N; i += blockDim.x) {
+        const int k = i / N, n = i % N;
+        sW[((k & 3) * N + n) * KV + (k >> 2)] = W[i];
+    }
     __syncthreads();
     const int lane = threadIdx.x & 31;
     const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    for (int64_t m = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; m < M; m += warps) {
-        const float4* hp = reinterpret_cast<const float4*>(H + m * K);
-        const float4* lp = Hlo ? reinterpret_cast<const float4*>(Hlo + m * K) : nullptr;
-        float acc[N];
+    const int64_t w0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    for (int64_t m = w0; m < M; m += 2 * warps) {
+        const int64_t m2 = m + warps;
+        const bool two = m2 < M;
+        const float4* hp0 = reinterpret_cast<const float4*>(H + m * K);
+        const float4* hp1 = reinterpret_cast<const float4*>(H + (two ? m2 : m) * K);
+        const float4* lp0 = HAS_LO ? reinterpret_cast<const float4*>(Hlo + m * K) : nullptr;
+        const float4* lp1 = HAS_LO ? reinterpret_cast<const float4*>(Hlo + (two ? m2 : m) * K) : nullptr;
+        float a0[N], a1[N];
 #pragma unroll
-        for (int n = 0; n < N; ++n) acc[n] = 0.0f;
-        for (int kv = lane; kv < (K >> 2); kv += 32) {
-            float4 h = hp[kv];
-            if (lp) { const float4 l = lp[kv]; h.x += l.x; h.y += l.y; h.z += l.z; h.w += l.w; }   // exact = hi + lo
-            const float hv[4] = {h.x, h.y, h.z, h.w};
+        for (int n = 0; n < N; ++n) { a0[n] = 0.0f; a1[n] = 0.0f; }
+        for (int kv = lane; kv < KV; kv += 32) {
+            float4 h0 = __ldcs(hp0 + kv), h1 = __ldcs(hp1 + kv);
+            if (HAS_LO) {   // exact activation = hi + lo
+                const float4 l0 = __ldcs(lp0 + kv), l1 = __ldcs(lp1 + kv);
+                h0.x += l0.x; h0.y += l0.y; h0.z += l0.z; h0.w += l0.w;
+                h1.x += l1.x; h1.y += l1.y; h1.z += l1.z; h1.w += l1.w;
+            }
+            const float v0[4] = {h0.x, h0.y, h0.z, h0.w};
+            const float v1[4] = {h1.x, h1.y, h1.z, h1.w};
 #pragma unroll
             for (int c = 0; c < 4; ++c)
 #pragma unroll
-                for (int n = 0; n < N; ++n) acc[n] = fmaf(hv[c], sW[(kv * 4 + c) * N + n], acc[n]);
+                for (int n = 0; n < N; ++n) {
+                    const float w = sW[(c * N + n) * KV + kv];
+                    a0[n] = fmaf(v0[c], w, a0[n]);
+                    a1[n] = fmaf(v1[c], w, a1[n]);
+                }
         }
 #pragma unroll
         for (int n = 0; n < N; ++n)
 #pragma unroll
-            for (int d = 16; d > 0; d >>= 1) acc[n] += __shfl_xor_sync(0xffffffffu, acc[n], d);
+            for (int d = 16; d > 0; d >>= 1) {
+                a0[n] += __shfl_xor_sync(0xffffffffu, a0[n], d);
+                a1[n] += __shfl_xor_sync(0xffffffffu, a1[n], d);
+            }
         if (lane == 0) {
 #pragma unroll
-            for (int n = 0; n < N; ++n) logits[m * N + n] = acc[n] + (bias ? bias[n] : 0.0f);
+            for (int n = 0; n < N; ++n) {
+                const float bn = bias ? bias[n] : 0.0f;
+                logits[m * N + n] = a0[n] + bn;
+                if (two) logits[m2 * N + n] = a1[n] + bn;
+            }
         }
     }
 }
 
-// one pass over H: dH = (dlogits W^T) .* leakyrelu'(H); per-CTA partial dW[k][n], db[n]
-template <int N, int KPT>   // KPT = ceil(K / 256) columns per thread
+__device__ __forceinline__ void tf32_split_dev(float a, float& hi, float& lo) {
+    uint32_t h, l;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(a));
+    hi = __uint_as_float(h);
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(a - hi));
+    lo = __uint_as_float(l);
+}
+
+// One pass over H (= hi (+ lo)): dH = (dlogits W^T) .* leakyrelu'(H), written either exact or as a tf32 hi/lo
+// pair (tensor-core mode); per-CTA partials of dW[k][n], db[n] and of the column sums of dH (= the bias
+// gradient of the layer below).  Partial layout per CTA: [K*N dW][N db][K colsum(dH)].
+template <int N, int KPT, bool HAS_LO>   // KPT = ceil(K / 256) columns per thread
 __global__ void __launch_bounds__(256)
 head_bwd_kernel(const float* __restrict__ H, const float* __restrict__ Hlo, const float* __restrict__ dlogits,
-                const float* __restrict__ W,
-                float* __restrict__ dH, float* __restrict__ partial, int64_t M, int K, float slope,
-                int64_t rows_per_cta, int need_dH) {
+                const float* __restrict__ W, float* __restrict__ dH, float* __restrict__ dHlo,
+                float* __restrict__ partial, int64_t M, int K, float slope, int64_t rows_per_cta, int need_dH) {
     const int tid = threadIdx.x;
-    float w[KPT][N], aw[KPT][N], ab[N];
+    float w[KPT][N], aw[KPT][N], ab[N], cs[KPT];
 #pragma unroll
-    for (int q = 0; q < KPT; ++q)
+    for (int q = 0; q < KPT; ++q) {
+        cs[q] = 0.0f;
 #pragma unroll
         for (int n = 0; n < N; ++n) {
             const int k = tid + q * 256;
             w[q][n] = (k < K) ? W[k * N + n] : 0.0f;
             aw[q][n] = 0.0f;
         }
+    }
 #pragma unroll
     for (int n = 0; n < N; ++n) ab[n] = 0.0f;
     const int64_t r0 = (int64_t)blockIdx.x * rows_per_cta;
@@ -288,7 +326,12 @@ head_bwd_kernel(const float* __restrict__ H, const float* __restrict__ Hlo, cons
 #pragma unroll
             for (int q = 0; q < KPT; ++q) {
                 const int k = tid + q * 256;
-                h[u][q] = (rv && k < K) ? (H[(m + u) * K + k] + (Hlo ? Hlo[(m + u) * K + k] : 0.0f)) : 0.0f;
+                float x = 0.0f;
+                if (rv && k < K) {
+                    x = __ldcs(H + (m + u) * K + k);
+                    if (HAS_LO) x += __ldcs(Hlo + (m + u) * K + k);
+                }
+                h[u][q] = x;
             }
 #pragma unroll
             for (int n = 0; n < N; ++n) d[u][n] = rv ? __ldg(dlogits + (m + u) * N + n) : 0.0f;
@@ -305,7 +348,18 @@ head_bwd_kernel(const float* __restrict__ H, const float* __restrict__ Hlo, cons
                     dx = fmaf(d[u][n], w[q][n], dx);
                     aw[q][n] = fmaf(h[u][q], d[u][n], aw[q][n]);
                 }
-                if (need_dH && rv && k < K) dH[(m + u) * K + k] = (h[u][q] > 0.0f) ? dx : slope * dx;
+                if (need_dH && rv && k < K) {
+                    const float g = (h[u][q] > 0.0f) ? dx : slope * dx;
+                    cs[q] += g;
+                    if (dHlo != nullptr) {
+                        float hi, lo;
+                        tf32_split_dev(g, hi, lo);
+                        dH[(m + u) * K + k] = hi;
+                        dHlo[(m + u) * K + k] = lo;
+                    } else {
+                        dH[(m + u) * K + k] = g;
+                    }
+                }
             }
             if (tid == 0) {
 #pragma unroll
@@ -313,13 +367,14 @@ head_bwd_kernel(const float* __restrict__ H, const float* __restrict__ Hlo, cons
             }
         }
     }
-    float* pw = partial + (int64_t)blockIdx.x * ((int64_t)K * N + N);
+    float* pw = partial + (int64_t)blockIdx.x * ((int64_t)K * N + N + K);
 #pragma unroll
     for (int q = 0; q < KPT; ++q) {
         const int k = tid + q * 256;
         if (k < K) {
 #pragma unroll
             for (int n = 0; n < N; ++n) pw[k * N + n] = aw[q][n];
+            pw[(int64_t)K * N + N + k] = cs[q];
         }
     }
     if (tid == 0) {
@@ -347,7 +402,7 @@ inline int64_t head_ctas(int64_t M) {
 
 size_t wgrad_partial_bytes(int64_t M, int K, int N) {
     size_t a = (size_t)wgrad_splits(M, K, N) * ((size_t)K * N + N) * sizeof(float);
-    size_t b = (size_t)head_ctas(M) * ((size_t)K * N + N) * sizeof(float);
+    size_t b = (size_t)head_ctas(M) * ((size_t)K * N + N + K) * sizeof(float);
     return a > b ? a : b;
 }
 
@@ -408,8 +463,11 @@ int launch_head_fwd(ppo_ctx* ctx, const float* H, const float* Hlo, const float*
     const int64_t cap = (int64_t)ctx->num_sms * 8;
     if (blocks > cap) blocks = cap;
     const size_t smem = (size_t)K * N * sizeof(float);
-#define PPO_HEAD_FWD(N_) \
-    case N_: head_fwd_kernel<N_><<<(unsigned)blocks, 256, smem, ctx->stream>>>(H, Hlo, W, bias, logits, M, K); break
+#define PPO_HEAD_FWD(N_)                                                                                          \
+    case N_:                                                                                                      \
+        if (Hlo) head_fwd_kernel<N_, true><<<(unsigned)blocks, 256, smem, ctx->stream>>>(H, Hlo, W, bias, logits, M, K); \
+        else head_fwd_kernel<N_, false><<<(unsigned)blocks, 256, smem, ctx->stream>>>(H, Hlo, W, bias, logits, M, K);    \
+        break
     switch (N) {
         PPO_HEAD_FWD(1); PPO_HEAD_FWD(2); PPO_HEAD_FWD(3); PPO_HEAD_FWD(4);
         PPO_HEAD_FWD(5); PPO_HEAD_FWD(6); PPO_HEAD_FWD(7); PPO_HEAD_FWD(8);
@@ -421,35 +479,45 @@ int launch_head_fwd(ppo_ctx* ctx, const float* H, const float* Hlo, const float*
 }
 
 int launch_head_bwd(ppo_ctx* ctx, const float* H, const float* Hlo, const float* dlogits, const float* W, float* dH,
-                    float* dW, float* db, int64_t M, int K, int N, float slope, float* partial, size_t partial_bytes,
-                    bool need_dH) {
+                    float* dHlo, float* dW, float* db, float* db_below, int64_t M, int K, int N, float slope,
+                    float* partial, size_t partial_bytes, bool need_dH) {
     if (N > 4 || K > 1024) {
-        PPO_REQUIRE(Hlo == nullptr, "head_bwd: hi/lo activations need N <= 4 and K <= 1024");
-        // generic path through the tile GEMMs
+        // generic path through the tile GEMMs (fp32 engine only)
+        PPO_REQUIRE(Hlo == nullptr && dHlo == nullptr && db_below == nullptr,
+                    "head_bwd: hi/lo activations need N <= 4 and K <= 1024");
         if (need_dH) PPO_TRY(launch_linear_dgrad_simt(ctx, dlogits, W, H, dH, M, K, N, slope));
         return launch_linear_wgrad_simt(ctx, H, dlogits, dW, db, M, K, N, partial, partial_bytes);
     }
     const int64_t ctas = head_ctas(M);
     const int64_t rows = ceil_div(M, ctas);
-    const size_t need = (size_t)ctas * ((size_t)K * N + N) * sizeof(float);
+    const int64_t stride = (int64_t)K * N + N + K;
+    const size_t need = (size_t)ctas * stride * sizeof(float);
     PPO_REQUIRE(need <= partial_bytes, "head_bwd: partial buffer too small (%zu > %zu)", need, partial_bytes);
     const int kpt = (int)ceil_div(K, 256);
-#define PPO_HEAD_BWD(N_, Q_)                                                                          \
-    if (N == N_ && kpt == Q_)                                                                          \
-        head_bwd_kernel<N_, Q_><<<(unsigned)ctas, 256, 0, ctx->stream>>>(H, Hlo, dlogits, W, dH, partial, M, K, \
-                                                                         slope, rows, need_dH ? 1 : 0)
-    PPO_HEAD_BWD(1, 1); PPO_HEAD_BWD(1, 2); PPO_HEAD_BWD(1, 3); PPO_HEAD_BWD(1, 4);
-    PPO_HEAD_BWD(2, 1); PPO_HEAD_BWD(2, 2); PPO_HEAD_BWD(2, 3); PPO_HEAD_BWD(2, 4);
-    PPO_HEAD_BWD(3, 1); PPO_HEAD_BWD(3, 2); PPO_HEAD_BWD(3, 3); PPO_HEAD_BWD(3, 4);
-    PPO_HEAD_BWD(4, 1); PPO_HEAD_BWD(4, 2); PPO_HEAD_BWD(4, 3); PPO_HEAD_BWD(4, 4);
+#define PPO_HEAD_BWD(N_, Q_)                                                                                   \
+    if (N == N_ && kpt == Q_) {                                                                                \
+        if (Hlo)                                                                                               \
+            head_bwd_kernel<N_, Q_, true><<<(unsigned)ctas, 256, 0, ctx->stream>>>(H, Hlo, dlogits, W, dH, dHlo, partial, \
+                                                                                   M, K, slope, rows, need_dH ? 1 : 0); \
+        else                                                                                                   \
+            head_bwd_kernel<N_, Q_, false><<<(unsigned)ctas, 256, 0, ctx->stream>>>(H, Hlo, dlogits, W, dH, dHlo, partial, \
+                                                                                    M, K, slope, rows, need_dH ? 1 : 0); \
+    }
+    PPO_HEAD_BWD(1, 1) PPO_HEAD_BWD(1, 2) PPO_HEAD_BWD(1, 3) PPO_HEAD_BWD(1, 4)
+    PPO_HEAD_BWD(2, 1) PPO_HEAD_BWD(2, 2) PPO_HEAD_BWD(2, 3) PPO_HEAD_BWD(2, 4)
+    PPO_HEAD_BWD(3, 1) PPO_HEAD_BWD(3, 2) PPO_HEAD_BWD(3, 3) PPO_HEAD_BWD(3, 4)
+    PPO_HEAD_BWD(4, 1) PPO_HEAD_BWD(4, 2) PPO_HEAD_BWD(4, 3) PPO_HEAD_BWD(4, 4)
 #undef PPO_HEAD_BWD
     ctx->launches += 1;
     PPO_CUDA(cudaGetLastError());
-    const int64_t stride = (int64_t)K * N + N;
     const int64_t cnt = (int64_t)K * N;
     reduce_partials_kernel<<<(unsigned)ceil_div(cnt, 256), 256, 0, ctx->stream>>>(partial, ctas, stride, cnt, dW);
     reduce_partials_kernel<<<1, 256, 0, ctx->stream>>>(partial + cnt, ctas, stride, N, db);
     ctx->launches += 2;
+    if (db_below != nullptr && need_dH) {
+        reduce_partials_kernel<<<(unsigned)ceil_div(K, 256), 256, 0, ctx->stream>>>(partial + cnt + N, ctas, stride, K, db_below);
+        ctx->launches += 1;
+    }
     PPO_CUDA(cudaGetLastError());
     return PPO_OK;
 }

@@ -190,6 +190,7 @@ struct KKParams {
     float slope;
     const float* bias;       // fwd
     const float* gate;       // dgrad: activation whose sign gates the gradient, [M][N]
+    float* colsum_partial;   // dgrad: [tiles_m][4][N] column sums of the output per 32-row quarter (or nullptr)
 };
 
 template <int BN>
@@ -358,6 +359,35 @@ tc_gemm_kk_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
                         for (int j = 0; j < 16; ++j)
                             if (col0 + j < p.N) v[j] = (__ldg(gp + j) > 0.0f) ? v[j] : p.slope * v[j];
                     }
+                }
+                if (p.colsum_partial != nullptr) {
+                    // column sums of this warp's 32 rows x 16 columns with a halving butterfly (16 shuffles):
+                    // = the bias gradient of the layer below, fused here so that dX is never re-read for it
+                    float k8[8], k4[4], k2[2], k1;
+                    const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4, b1 = lane & 2;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float send = b4 ? v[i] : v[i + 8];
+                        k8[i] = (b4 ? v[i + 8] : v[i]) + __shfl_xor_sync(0xffffffffu, send, 16);
+                    }
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float send = b3 ? k8[i] : k8[i + 4];
+                        k4[i] = (b3 ? k8[i + 4] : k8[i]) + __shfl_xor_sync(0xffffffffu, send, 8);
+                    }
+#pragma unroll
+                    for (int i = 0; i < 2; ++i) {
+                        const float send = b2 ? k4[i] : k4[i + 2];
+                        k2[i] = (b2 ? k4[i + 2] : k4[i]) + __shfl_xor_sync(0xffffffffu, send, 4);
+                    }
+                    {
+                        const float send = b1 ? k2[0] : k2[1];
+                        k1 = (b1 ? k2[1] : k2[0]) + __shfl_xor_sync(0xffffffffu, send, 2);
+                    }
+                    k1 += __shfl_xor_sync(0xffffffffu, k1, 1);
+                    const int cidx = (b4 ? 8 : 0) + (b3 ? 4 : 0) + (b2 ? 2 : 0) + (b1 ? 1 : 0);
+                    if ((lane & 1) == 0 && col0 + cidx < p.N)
+                        p.colsum_partial[((size_t)(tile / p.tiles_n) * 4 + q) * p.N + col0 + cidx] = k1;
                 }
                 if (storer) bulk_wait_read0();        // the group's previous TMA stores have read its staging tile
                 named_bar_sync(1 + grp, 64);
@@ -577,6 +607,22 @@ tc_reduce_partials_kernel(const float* __restrict__ partial, int splits, int64_t
     }
 }
 
+// stage 1 of folding the dgrad epilogue's per-quarter column sums: block (x = column block, y = row chunk)
+__global__ void __launch_bounds__(256)
+colsum_fold_kernel(const float* __restrict__ part, int64_t rows, int N, int64_t rows_per_chunk, float* __restrict__ out) {
+    const int n = blockIdx.x * 256 + threadIdx.x;
+    if (n >= N) return;
+    const int64_t r0 = (int64_t)blockIdx.y * rows_per_chunk;
+    const int64_t r1 = r0 + rows_per_chunk < rows ? r0 + rows_per_chunk : rows;
+    float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
+    int64_t r = r0;
+    for (; r + 3 < r1; r += 4) {
+        s0 += part[r * N + n]; s1 += part[(r + 1) * N + n]; s2 += part[(r + 2) * N + n]; s3 += part[(r + 3) * N + n];
+    }
+    for (; r < r1; ++r) s0 += part[r * N + n];
+    out[(size_t)blockIdx.y * N + n] = (s0 + s1) + (s2 + s3);
+}
+
 // column sums of dY_hi + dY_lo [M][N] (bias gradient): per-CTA partials over a row range
 __global__ void __launch_bounds__(256)
 colsum_kernel(const float* __restrict__ dY, const float* __restrict__ dYlo, int64_t M, int N, int64_t rows_per_cta,
@@ -698,8 +744,9 @@ size_t tc_partial_bytes(int64_t tokens, int K, int N, int num_sms) {
     const int BN = N > 128 ? 256 : 128;
     const int tiles = (int)(ceil_div(K, TC_BM) * ceil_div(N, BN));
     const size_t a = (size_t)wgrad_splits_tc(tokens, tiles, num_sms) * K * N * 4;
-    const size_t b = (size_t)num_sms * 4 * N * 4;   // colsum partials
-    return std::max(a, b);
+    const size_t b = (size_t)num_sms * 4 * N * 4;   // stand-alone colsum partials
+    const size_t c = ((size_t)4 * ceil_div(tokens, TC_BM) + 64) * (size_t)std::max(K, N) * 4;   // dgrad-epilogue column sums
+    return std::max(a, std::max(b, c));
 }
 
 int ensure_tc_workspace(ppo_policy* p, int64_t tokens) {
@@ -777,6 +824,18 @@ int launch_mn(ppo_ctx* ctx, const float* X, const float* X_lo, const float* dY, 
     const int grid = p.tiles_k * p.tiles_n * splits;
     tc_gemm_mn_kernel<BN><<<grid, TC_THREADS, smem, ctx->stream>>>(mA, mAl, mB, mBl, p);
     ctx->launches += 1;
+    PPO_CUDA(cudaGetLastError());
+    return PPO_OK;
+}
+
+// fold [rows][N] per-quarter column sums (rows = 4 * tiles_m) into out[N]; scratch holds 64 * N floats
+int fold_colsum(ppo_ctx* ctx, const float* part, int64_t rows, int N, float* scratch, float* out) {
+    const int chunks = (int)std::min<int64_t>(64, rows);
+    const int64_t rpc = ceil_div(rows, chunks);
+    dim3 grid((unsigned)ceil_div(N, 256), (unsigned)chunks);
+    colsum_fold_kernel<<<grid, 256, 0, ctx->stream>>>(part, rows, N, rpc, scratch);
+    tc_reduce_partials_kernel<<<(unsigned)ceil_div(N, 256), 256, 0, ctx->stream>>>(scratch, chunks, N, N, out);
+    ctx->launches += 2;
     PPO_CUDA(cudaGetLastError());
     return PPO_OK;
 }
@@ -879,28 +938,38 @@ int tc_linear_fwd(ppo_policy* p, int l, const float* X, float* Y, int64_t M) {
     return kk_dispatch(ctx, A_hi, A_lo, ly.WT_hi, ly.WT_lo, Y, st->act_lo[l + 1], M, N, K, kp);
 }
 
-int tc_linear_bwd(ppo_policy* p, int l, const float* X, const float* dY, float* dX, float* dW, float* db, int64_t M) {
+int tc_linear_bwd(ppo_policy* p, int l, const float* X, const float* dY, float* dX, float* dW, float* db_below, int64_t M) {
+    // dY arrives as a tf32 hi/lo pair (written by head_bwd or by the dgrad epilogue of the layer above), and its
+    // column sums (this layer's bias gradient) were already produced by that same kernel.
     TcState* st = state(p);
     ppo_ctx* ctx = p->ctx;
     PPO_TRY(ensure_tc_workspace(p, p->ws_tokens > M ? p->ws_tokens : M));
     const int K = p->dims[l], N = p->dims[l + 1];
     TcLayer& ly = st->layers[l];
     PPO_REQUIRE(dY == p->dact[0] || dY == p->dact[1], "tc_linear_bwd: unexpected gradient buffer");
-    float* dY_hi = const_cast<float*>(dY);
-    float* dY_lo = (dY == p->dact[0]) ? st->dact_lo[0] : st->dact_lo[1];
-    // the gradient entering the last hidden layer was produced in fp32 by the head kernel: split it in place
-    if (l == p->L - 2) PPO_TRY(split(ctx, dY, dY_hi, dY_lo, M * N));
+    const float* dY_lo = (dY == p->dact[0]) ? st->dact_lo[0] : st->dact_lo[1];
     const float* X_hi = (l == 0) ? st->x_hi : X;
     const float* X_lo = (l == 0) ? st->x_lo : st->act_lo[l];
-    PPO_TRY(wgrad_tc(ctx, X_hi, X_lo, dY_hi, dY_lo, dW, db, st->partial, st->partial_bytes, M, K, N));
+    PPO_TRY(wgrad_tc(ctx, X_hi, X_lo, dY, dY_lo, dW, nullptr, st->partial, st->partial_bytes, M, K, N));
     if (dX != nullptr) {
         float* dX_lo = (dX == p->dact[0]) ? st->dact_lo[0] : st->dact_lo[1];
         KKParams kp{};
         kp.epi = TC_EPI_DGRAD; kp.act = 0; kp.slope = p->slope; kp.bias = nullptr; kp.gate = X_hi;
+        kp.colsum_partial = (db_below != nullptr) ? st->partial : nullptr;
         // dX[M, K] = dY[M, N] * W[K, N]^T : A = dY (K-major in N), B = W rows (K-major in N)
-        PPO_TRY(kk_dispatch(ctx, dY_hi, dY_lo, ly.W_hi, ly.W_lo, dX, dX_lo, M, K, N, kp));
+        PPO_TRY(kk_dispatch(ctx, dY, dY_lo, ly.W_hi, ly.W_lo, dX, dX_lo, M, K, N, kp));
+        if (db_below != nullptr) {
+            const int64_t rows = 4 * ceil_div(M, TC_BM);
+            PPO_TRY(fold_colsum(ctx, st->partial, rows, K, st->partial + (size_t)rows * K, db_below));
+        }
     }
     return PPO_OK;
+}
+
+float* tc_dact_lo(ppo_policy* p, const float* dact) {
+    TcState* st = state(p);
+    if (st == nullptr) return nullptr;
+    return (dact == p->dact[0]) ? st->dact_lo[0] : st->dact_lo[1];
 }
 
 void tc_destroy(ppo_policy* p) {
@@ -925,11 +994,17 @@ int tc_test_fwd(ppo_ctx* ctx, const float* X_hi, const float* X_lo, const float*
     return kk_dispatch(ctx, X_hi, X_lo, WT_hi, WT_lo, Y_hi, Y_lo, M, N, K, kp);
 }
 int tc_test_dgrad(ppo_ctx* ctx, const float* dY_hi, const float* dY_lo, const float* W_hi, const float* W_lo, const float* gate,
-                  float* dX_hi, float* dX_lo, int64_t M, int K, int N, float slope) {
+                  float* dX_hi, float* dX_lo, int64_t M, int K, int N, float slope, float* colsum_scratch, float* colsum_out) {
     PPO_TRY(load_encode());
     KKParams kp{};
     kp.epi = TC_EPI_DGRAD; kp.slope = slope; kp.gate = gate;
-    return kk_dispatch(ctx, dY_hi, dY_lo, W_hi, W_lo, dX_hi, dX_lo, M, K, N, kp);
+    kp.colsum_partial = colsum_out ? colsum_scratch : nullptr;
+    PPO_TRY(kk_dispatch(ctx, dY_hi, dY_lo, W_hi, W_lo, dX_hi, dX_lo, M, K, N, kp));
+    if (colsum_out) {
+        const int64_t rows = 4 * ceil_div(M, TC_BM);
+        PPO_TRY(fold_colsum(ctx, colsum_scratch, rows, K, colsum_scratch + (size_t)rows * K, colsum_out));
+    }
+    return PPO_OK;
 }
 int tc_test_wgrad(ppo_ctx* ctx, const float* X_hi, const float* X_lo, const float* dY_hi, const float* dY_lo, float* dW,
                   float* db, float* partial, size_t partial_bytes, int64_t M, int K, int N) {
