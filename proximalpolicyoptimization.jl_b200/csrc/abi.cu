@@ -277,6 +277,7 @@ int append_common(ppo_buf* buf, int64_t n, const void* feat, bool feat_i64, cons
     PPO_TRY(h2d(ctx, buf->old_prob + off, old_prob, (size_t)n * 4));
     PPO_TRY(h2d(ctx, buf->reward + off, reward, (size_t)n * 4));
     PPO_TRY(h2d(ctx, buf->terminal + off, terminal, (size_t)n));
+    PPO_TRY(launch_normalize_bool(ctx, buf->terminal + off, n));   // any non-zero byte is `true`; the scan assumes 0/1
     PPO_TRY(h2d(ctx, d_act, action, (size_t)n * 8));
     PPO_TRY(launch_convert_actions_in(ctx, d_act, buf->action + off, n, buf->A, d_bad));
     PPO_TRY(check_bad_flag(ctx, d_bad, "append: selected action outside 1..A"));
@@ -390,10 +391,11 @@ int ppo_buffer_create(ppo_ctx* ctx, int64_t capacity, int nf, int nhe, int apa, 
         (s = dev_alloc(&b->action, (size_t)capacity)) != PPO_OK ||
         (s = dev_alloc(&b->old_prob, (size_t)capacity)) != PPO_OK ||
         (s = dev_alloc(&b->reward, (size_t)cap16)) != PPO_OK ||
+        (s = dev_alloc(&b->reward_alt, (size_t)cap16)) != PPO_OK ||
         (s = dev_alloc(&b->terminal, (size_t)cap16)) != PPO_OK ||
         (s = dev_alloc(&b->perm, (size_t)capacity)) != PPO_OK ||
         (s = dev_alloc(&b->d_norm, 2)) != PPO_OK ||
-        (s = dev_alloc(&b->d_tile_stats, (size_t)2 * ceil_div(capacity, SCAN_TILE))) != PPO_OK) {
+        (s = dev_alloc(&b->d_tile_stats, (size_t)2 * SCAN_STATS_PER_TILE * ceil_div(capacity, SCAN_TILE))) != PPO_OK) {
         ppo_buffer_destroy(b);
         return s;
     }
@@ -406,7 +408,7 @@ int ppo_buffer_destroy(ppo_buf* b) {
     cudaSetDevice(b->ctx->device);
     cudaStreamSynchronize(b->ctx->stream);
     dev_free(b->feat); dev_free(b->mask); dev_free(b->action); dev_free(b->old_prob); dev_free(b->reward);
-    dev_free(b->terminal); dev_free(b->perm); dev_free(b->reward_saved); dev_free(b->d_norm); dev_free(b->d_tile_stats);
+    dev_free(b->terminal); dev_free(b->perm); dev_free(b->reward_saved); dev_free(b->reward_alt); dev_free(b->d_norm); dev_free(b->d_tile_stats);
     free_batch(b->batch);
     delete b;
     return PPO_OK;
@@ -440,9 +442,10 @@ int ppo_compute_returns(ppo_buf* buf, double discount, int discount_is_f32) {
     PPO_TRY(use(ctx));
     if (buf->n == 0) return PPO_OK;
     PPO_TRY(ensure_scratch(ctx, scan_scratch_bytes(buf->n)));
-    PPO_TRY(launch_returns_scan(ctx, buf->reward, buf->terminal, buf->n, discount, discount_is_f32,
+    PPO_TRY(launch_returns_scan(ctx, buf->reward, buf->reward_alt, buf->terminal, buf->n, discount, discount_is_f32,
                                 buf->d_tile_stats, ctx->d_scratch));
-    buf->n_tiles_stats = ceil_div(buf->n, SCAN_TILE);
+    std::swap(buf->reward, buf->reward_alt);      // rollouts.rewards .= returns
+    buf->n_tiles_stats = SCAN_STATS_PER_TILE * ceil_div(buf->n, SCAN_TILE);
     buf->stats_valid = true;
     if (buf->normalize)
         PPO_TRY(launch_norm_finalize(ctx, buf->d_tile_stats, buf->n_tiles_stats, buf->n, buf->norm_eps, buf->d_norm));

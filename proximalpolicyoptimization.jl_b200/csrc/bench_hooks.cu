@@ -10,6 +10,7 @@
 #include "gemm_tc.cuh"
 
 namespace ppo {
+extern int g_scan_dbg;
 namespace {
 
 __device__ __forceinline__ uint32_t hash32(uint64_t x) {
@@ -109,30 +110,19 @@ extern "C" int ppo_bench_kernel(ppo_ctx* ctx, const char* which, int64_t n, int 
     Scope sc;
     const std::string w(which);
     if (w == "scan") {
-        float* r; uint8_t* t; double* stats;
+        float *r, *o; uint8_t* t; double* stats;
         const int64_t n16 = round_up(n, SCAN_TILE);
-        PPO_TRY(sc.alloc(&r, (size_t)n16)); PPO_TRY(sc.alloc(&t, (size_t)n16));
-        PPO_TRY(sc.alloc(&stats, (size_t)2 * ceil_div(n, SCAN_TILE)));
+        PPO_TRY(sc.alloc(&r, (size_t)n16)); PPO_TRY(sc.alloc(&o, (size_t)n16)); PPO_TRY(sc.alloc(&t, (size_t)n16));
+        PPO_TRY(sc.alloc(&stats, (size_t)2 * SCAN_STATS_PER_TILE * ceil_div(n, SCAN_TILE)));
         void* scratch; PPO_TRY(sc.alloc((char**)&scratch, scan_scratch_bytes(n)));
         PPO_TRY(fill(ctx, r, n, 1, 1, 11));
         fill_terminal_kernel<<<148 * 8, 256, 0, ctx->stream>>>(t, n, a > 0 ? a : 15, 12);
         const double disc = (b == 0) ? 1.0 : 0.99;
-        // rewards are overwritten by returns every launch; with |r| <= 4 and episodes of ~a steps the values
-        // stay finite over the few launches timed here only if we refill: refill outside the timed region.
-        auto launch = [&]() -> int { return launch_returns_scan(ctx, r, t, n, disc, 0, stats, scratch); };
-        PPO_CUDA(cudaEventCreate(&sc.e0)); PPO_CUDA(cudaEventCreate(&sc.e1));
-        double total = 0.0;
-        for (int it = -3; it < iters; ++it) {
-            PPO_TRY(fill(ctx, r, n, 1, 1, 11));
-            if (flush_l2_flag) PPO_TRY(flush_l2(ctx));
-            PPO_CUDA(cudaEventRecord(sc.e0, ctx->stream));
-            PPO_TRY(launch());
-            PPO_CUDA(cudaEventRecord(sc.e1, ctx->stream));
-            PPO_CUDA(cudaEventSynchronize(sc.e1));
-            float ms = 0.0f; PPO_CUDA(cudaEventElapsedTime(&ms, sc.e0, sc.e1));
-            if (it >= 0) total += ms;
-        }
-        *ms_out = total / iters;
+        g_scan_dbg = c;   // timing experiments only (1: skip look-back, 4: skip stats, 8: no look-ahead)
+        int st = time_loop(ctx, sc, iters, flush_l2_flag,
+                           [&]() { return launch_returns_scan(ctx, r, o, t, n, disc, 0, stats, scratch); }, ms_out);
+        g_scan_dbg = 0;
+        PPO_TRY(st);
         *work_out = 9.0 * (double)n;
         return PPO_OK;
     }

@@ -81,7 +81,8 @@ struct ppo_buf {
     float* mask = nullptr;       // [cap][A]
     int* action = nullptr;       // [cap], 0-based on the device
     float* old_prob = nullptr;   // [cap]
-    float* reward = nullptr;     // [cap]; overwritten in place by returns
+    float* reward = nullptr;     // [cap]; rewards, then returns (compute_state_value! swaps it with reward_alt)
+    float* reward_alt = nullptr; // [cap]; output array of the next returns scan
     float* reward_saved = nullptr; // optional snapshot of the raw rewards
     int64_t saved_n = 0;
     uint8_t* terminal = nullptr; // [cap]
@@ -141,11 +142,12 @@ namespace ppo {
 constexpr int SCAN_THREADS = 256;
 constexpr int SCAN_ITEMS = 16;
 constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+constexpr int SCAN_STATS_PER_TILE = SCAN_THREADS / 32;   // one {sum, sumsq} pair per warp
 
 // scan.cu (K1, K2)
 size_t scan_scratch_bytes(int64_t n);
-int launch_returns_scan(ppo_ctx* ctx, float* reward_inout, const uint8_t* terminal, int64_t n,
-                        double discount, int discount_is_f32, double* tile_stats, void* scratch);
+int launch_returns_scan(ppo_ctx* ctx, const float* reward_in, float* returns_out, const uint8_t* terminal,
+                        int64_t n, double discount, int discount_is_f32, double* tile_stats, void* scratch);
 int launch_norm_finalize(ppo_ctx* ctx, const double* tile_stats, int64_t n_tiles, int64_t n,
                          double eps, float* d_norm);
 
@@ -169,6 +171,7 @@ int launch_convert_actions_in(ppo_ctx* ctx, const int64_t* a1, int* a0, int64_t 
 int launch_convert_actions_out(ppo_ctx* ctx, const int* a0, int64_t* a1, int64_t n);
 int launch_linear_index_in(ppo_ctx* ctx, const int64_t* lin1, int* a0, int64_t n, int A, int* d_bad);
 int launch_i64_to_f32(ppo_ctx* ctx, const int64_t* src, float* dst, int64_t n);
+int launch_normalize_bool(ppo_ctx* ctx, uint8_t* t, int64_t n);
 
 // loss.cu (K6)
 int64_t loss_num_blocks(int64_t nb, int A);

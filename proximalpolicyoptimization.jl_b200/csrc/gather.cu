@@ -224,6 +224,13 @@ linear_in_kernel(const int64_t* __restrict__ lin1, int* __restrict__ a0, int64_t
 }
 
 __global__ void __launch_bounds__(256)
+normalize_bool_kernel(uint8_t* __restrict__ t, int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (int64_t)gridDim.x * blockDim.x)
+        t[i] = t[i] != 0 ? 1 : 0;
+}
+
+__global__ void __launch_bounds__(256)
 i64_to_f32_kernel(const int64_t* __restrict__ s, float* __restrict__ d, int64_t n) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
          i += (int64_t)gridDim.x * blockDim.x)
@@ -304,6 +311,14 @@ int launch_convert_actions_out(ppo_ctx* ctx, const int* a0, int64_t* a1, int64_t
 int launch_linear_index_in(ppo_ctx* ctx, const int64_t* lin1, int* a0, int64_t n, int A, int* d_bad) {
     if (n <= 0) return PPO_OK;
     linear_in_kernel<<<grid_for(ctx, n, 256), 256, 0, ctx->stream>>>(lin1, a0, n, A, d_bad);
+    ctx->launches += 1;
+    PPO_CUDA(cudaGetLastError());
+    return PPO_OK;
+}
+
+int launch_normalize_bool(ppo_ctx* ctx, uint8_t* t, int64_t n) {
+    if (n <= 0) return PPO_OK;
+    normalize_bool_kernel<<<grid_for(ctx, n, 256), 256, 0, ctx->stream>>>(t, n);
     ctx->launches += 1;
     PPO_CUDA(cudaGetLastError());
     return PPO_OK;

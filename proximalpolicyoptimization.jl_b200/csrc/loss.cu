@@ -35,6 +35,17 @@ __device__ __forceinline__ float group_sum(float v) {
     return v;
 }
 
+// exp(x) for x <= 0 with ~1 ulp error in 6 instructions: 2^(x log2 e) with the product carried in two floats,
+// so the argument reduction error of the bare ex2.approx path (|x| * 2^-24) is removed.
+__device__ __forceinline__ float fast_exp_neg(float x) {
+    const float L2E_HI = 1.4426950216293335f, L2E_LO = 1.9259629911e-8f;
+    const float t = x * L2E_HI;
+    const float r = fmaf(x, L2E_LO, fmaf(x, L2E_HI, -t));        // low part of x * log2(e)
+    const float e = exp2f(t);                                       // ex2.approx (2 ulp)
+    return (e == 0.0f) ? 0.0f : fmaf(e * 0.6931471805599453f, r, e);   // e 2^r ~= e (1 + r ln 2); exp(-inf) = 0 exactly
+}
+__device__ __forceinline__ float fast_log(float x) { return __logf(x); }   // lg2.approx * ln 2: abs err ~1e-7 on [-24, 0]
+
 struct LossArgs {
     const float* logits; const float* mask; const int* action; const float* old_prob; const float* adv;
     int64_t nb; int A;
@@ -106,8 +117,9 @@ loss_vec_kernel(LossArgs a) {
 #pragma unroll
         for (int v = 0; v < V; ++v)
 #pragma unroll
-            for (int c = 0; c < 4; ++c) { z[v][c] = expf(z[v][c] - mx); sum += z[v][c]; }
+            for (int c = 0; c < 4; ++c) { z[v][c] = fast_exp_neg(z[v][c] - mx); sum += z[v][c]; }
         sum = group_sum<G>(sum);
+        const float inv_sum = __frcp_rn(sum);
 
         const int act = a.action[bb];
         const int act_vec = act >> 2, act_c = act & 3;
@@ -118,10 +130,10 @@ loss_vec_kernel(LossArgs a) {
         for (int v = 0; v < V; ++v)
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
-                const float p = __fdiv_rn(z[v][c], sum);
+                const float p = z[v][c] * inv_sum;
                 z[v][c] = p;
                 const float ps = p + a.smooth_over_A;
-                const float lg = logf(ps);
+                const float lg = fast_log(ps);
                 ent = fmaf(ps, lg, ent);
                 g[v][c] = a.c_ent * (lg + 1.0f);
                 if (v == owner_v && c == act_c) sel_local = p;

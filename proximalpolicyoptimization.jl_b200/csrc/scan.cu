@@ -5,16 +5,22 @@
 //     v <- rewards[i] + discount * (terminal[i] ? 0 : v_next)        for i = n .. 1
 // Each transition is the affine map c -> b_i + a_i c with (a_i, b_i) = (terminal_i ? 0 : g, r_i);
 // the scan composes maps right to left.  One pass over HBM (read 4 B reward + 1 B terminal,
-// write 4 B return = 9 B/transition): single-pass chained scan with decoupled look-back,
-// tiles handed out right-to-left by an atomic ticket so a tile only ever waits on tiles that
-// are already resident.  The carry is Float64 exactly like Julia's promoted `v` (the reference
+// write 4 B return = 9 B/transition): single-pass chained scan with decoupled look-back.
+// Tile ids are blockIdx.x counted from the RIGHT end (the scan runs right to left), so a tile
+// only waits on lower-numbered blocks, which the hardware dispatches first (the forward-progress
+// assumption CUB's DeviceScan makes).  A global atomic ticket was measured to serialise at ~27
+// cycles per tile (0.23 of the 0.31 ms for 64 M transitions) and was removed.  The carry is Float64 exactly like Julia's promoted `v` (the reference
 // passes a Float64 discount everywhere); inside a thread's 16-item chunk the recurrence is the
 // reference's serial loop with unfused multiply/add, so any chunk that starts right of an
 // episode end is bit-identical to the serial result, and with discount == 1 and integer
 // rewards every value is exact.
 //
+// The kernel runs out of place (the rollout buffer swaps its reward/return arrays afterwards, which is what
+// `rollouts.rewards .= compute_returns(...)` amounts to).
 // Memory layout: rewards float[n], terminal uint8[n]; thread t of a tile owns 16 consecutive
 // transitions = 4 x LDG.128 + 1 x LDG.128 in flight, 4 x STG.128 out.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace ppo {
@@ -62,166 +68,296 @@ __host__ __device__ inline ScanScratch carve(void* scratch, int64_t tiles) {
     return s;
 }
 
+constexpr int SCAN_LOOK = 128;   // transitions right of the tile inspected for an episode end (4 per lane of warp 0)
+
+// one pipeline stage in shared memory: the tile's rewards in the padded blocked arrangement, its terminals, and
+// the look-ahead window
+// float offset of 16-byte piece j (0..3) of chunk c (0..31) inside a warp's region (chunks padded to 20 floats)
+__device__ __forceinline__ int sx_off(int c, int j) { return c * 20 + j * 4; }
+
+struct __align__(16) ScanStage {
+    float x[SCAN_THREADS / 32][32 * 20];     // per warp: 32 chunks of 16 items padded to 20 floats (conflict-free)
+    uint8_t t[SCAN_TILE];
+    float lx[SCAN_LOOK];
+    uint8_t lt[SCAN_LOOK];
+};
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// Persistent CTAs: block b scans tiles b, b + G, b + 2G, ... (tile ids count from the RIGHT end, the direction of the
+// scan), G = all co-resident CTAs.  While tile i is being scanned, the cp.async copies of tile i+1 are in flight, so
+// HBM always has work queued; before this software pipeline the kernel was latency bound at ~55 % of the roofline.
 template <bool F32CARRY>
-__global__ void __launch_bounds__(SCAN_THREADS)
-returns_scan_kernel(float* __restrict__ rew, const uint8_t* __restrict__ term, int64_t n, double g,
-                    int tiles, ScanScratch sc, double* __restrict__ tile_stats) {
-    __shared__ int s_tile;
-    __shared__ double sA[SCAN_THREADS / 32], sB[SCAN_THREADS / 32];
-    __shared__ double s_carry;
-    __shared__ double s_sum[SCAN_THREADS / 32], s_sq[SCAN_THREADS / 32];
+__global__ void __launch_bounds__(SCAN_THREADS, 4)
+returns_scan_kernel(const float* __restrict__ rew, float* __restrict__ out, const uint8_t* __restrict__ term, int64_t n,
+                    double g, double g8, int tiles, ScanScratch sc, double* __restrict__ tile_stats, int dbg) {
+    extern __shared__ __align__(16) unsigned char scan_smem[];
+    ScanStage* stages = reinterpret_cast<ScanStage*>(scan_smem);
+    // block-shared scratch, double-buffered by iteration parity: with a single __syncthreads per tile a warp can
+    // run at most one barrier ahead of the slowest warp, so parity buffering rules out write-after-read races
+    __shared__ double sA2[2][SCAN_THREADS / 32], sB2[2][SCAN_THREADS / 32];
+    __shared__ double s_carry2[2];
+    __shared__ double s_lookA2[2], s_lookB2[2];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) s_tile = atomicAdd(sc.counter, 1);
-    __syncthreads();
-    const int t = s_tile;                       // ticket: 0 = right-most tile
-    const int tile_idx = tiles - 1 - t;         // position from the left
-    const int64_t base = (int64_t)tile_idx * SCAN_TILE + (int64_t)tid * SCAN_ITEMS;
-
-    float r[SCAN_ITEMS];
-    uint32_t tm[SCAN_ITEMS / 4];
-    if (base + SCAN_ITEMS <= n) {
-        const float4* rp = reinterpret_cast<const float4*>(rew + base);
-#pragma unroll
-        for (int q = 0; q < SCAN_ITEMS / 4; ++q) {
-            float4 v = __ldcs(rp + q);
-            r[4 * q + 0] = v.x; r[4 * q + 1] = v.y; r[4 * q + 2] = v.z; r[4 * q + 3] = v.w;
-        }
-        uint4 tv = __ldcs(reinterpret_cast<const uint4*>(term + base));
-        tm[0] = tv.x; tm[1] = tv.y; tm[2] = tv.z; tm[3] = tv.w;
-    } else {
-#pragma unroll
-        for (int q = 0; q < SCAN_ITEMS / 4; ++q) tm[q] = 0;
-#pragma unroll
-        for (int i = 0; i < SCAN_ITEMS; ++i) {
-            int64_t idx = base + i;
-            bool in = idx < n;
-            r[i] = in ? rew[idx] : 0.0f;
-            uint32_t tb = in ? (term[idx] != 0) : 1u;   // padding behaves like an episode end
-            tm[i >> 2] |= tb << (8 * (i & 3));
-        }
-    }
-    auto is_term = [&](int i) -> bool { return ((tm[i >> 2] >> (8 * (i & 3))) & 0xffu) != 0; };
-
-    // 1. per-thread aggregate map, right to left (B is the serial recurrence with zero carry)
-    Map me{1.0, 0.0};
-#pragma unroll
-    for (int i = SCAN_ITEMS - 1; i >= 0; --i) {
-        double a = is_term(i) ? 0.0 : g;
-        me.B = __dadd_rn((double)r[i], __dmul_rn(a, me.B));
-        me.A = a * me.A;
-    }
-
-    // 2. reverse inclusive scan over the lanes of the warp (lane l: lanes l..31)
-    Map inc = me;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        Map o;
-        o.A = __shfl_down_sync(0xffffffffu, inc.A, d);
-        o.B = __shfl_down_sync(0xffffffffu, inc.B, d);
-        if (lane + d < 32) inc = compose(inc, o);
-    }
-    Map lane_excl;  // lanes l+1..31
-    lane_excl.A = __shfl_down_sync(0xffffffffu, inc.A, 1);
-    lane_excl.B = __shfl_down_sync(0xffffffffu, inc.B, 1);
-    if (lane == 31) { lane_excl.A = 1.0; lane_excl.B = 0.0; }
-    if (lane == 0) { sA[warp] = inc.A; sB[warp] = inc.B; }
-    __syncthreads();
-
-    // 3. maps of the warps to the right of this one (warp+1 .. last)
     constexpr int NW = SCAN_THREADS / 32;
-    Map warp_excl{1.0, 0.0};
-    for (int k = NW - 1; k > warp; --k) warp_excl = compose(Map{sA[k], sB[k]}, warp_excl);
 
-    // 4. tile aggregate, publication and look-back (thread 0)
-    if (tid == 0) {
-        Map tile = compose(Map{sA[0], sB[0]}, warp_excl);
-        double carry = 0.0;
-        if (t == 0) {
-            sc.incl[0] = tile.B;
-            __threadfence();
-            st_release_i32(sc.flags + 0, 2);
-        } else {
-            if (tile.A == 0.0) {   // an episode ends inside the tile: inclusive value known already
-                sc.incl[t] = tile.B;
-                __threadfence();
-                st_release_i32(sc.flags + t, 2);
-            } else {
-                sc.aggA[t] = tile.A; sc.aggB[t] = tile.B;
-                __threadfence();
-                st_release_i32(sc.flags + t, 1);
+    // issue the asynchronous copies of tile t into a stage (full tiles only; the single partial tile, t == 0 when
+    // n is not a multiple of the tile, is read directly below)
+    auto issue = [&](int t, ScanStage& st) {
+        const int tile_idx = tiles - 1 - t;
+        const int64_t tile_base = (int64_t)tile_idx * SCAN_TILE;
+        if (tile_base + SCAN_TILE <= n) {
+            const float* src = rew + tile_base + (int64_t)warp * (32 * SCAN_ITEMS);
+#pragma unroll
+            for (int q = 0; q < SCAN_ITEMS / 4; ++q)      // element e = 128 q + 4 lane of the warp's 512
+                cp_async16(&st.x[warp][sx_off(q * 8 + (lane >> 2), lane & 3)], src + q * 128 + 4 * lane);
+            cp_async16(&st.t[tid * SCAN_ITEMS], term + tile_base + (int64_t)tid * SCAN_ITEMS);
+            if (warp == 0) {
+                const int64_t e0 = tile_base + SCAN_TILE + 4 * lane;
+                if (e0 + 4 <= n) {
+                    cp_async16(&st.lx[4 * lane], rew + e0);
+                    cp_async4(&st.lt[4 * lane], term + e0);
+                }
             }
-            Map cur{1.0, 0.0};
-            int j = t - 1;
-            while (true) {
-                int f;
-                while ((f = ld_acquire_i32(sc.flags + j)) == 0) { __nanosleep(20); }
-                if (f == 2) { carry = __dadd_rn(cur.B, __dmul_rn(cur.A, __ldcg(sc.incl + j))); break; }
-                cur = compose(cur, Map{__ldcg(sc.aggA + j), __ldcg(sc.aggB + j)});
-                if (cur.A == 0.0) { carry = cur.B; break; }
-                --j;   // j >= 0 always holds: ticket 0 publishes an inclusive value
+        }
+        cp_async_commit();
+    };
+
+    int t = (int)blockIdx.x;
+    if (t < tiles) issue(t, stages[0]);
+    for (int it = 0; t < tiles; t += (int)gridDim.x, ++it) {
+        ScanStage& st = stages[it & 1];
+        double* sA = sA2[it & 1];
+        double* sB = sB2[it & 1];
+        double& s_lookA = s_lookA2[it & 1];
+        double& s_lookB = s_lookB2[it & 1];
+        double& s_carry = s_carry2[it & 1];
+        const int t_next = t + (int)gridDim.x;
+        if (t_next < tiles) { issue(t_next, stages[(it + 1) & 1]); cp_async_wait<1>(); }
+        else cp_async_wait<0>();
+        __syncwarp();
+
+        const int tile_idx = tiles - 1 - t;         // position from the left
+        const int64_t tile_base = (int64_t)tile_idx * SCAN_TILE;
+        const bool full_tile = tile_base + SCAN_TILE <= n;
+        const int64_t base = tile_base + (int64_t)tid * SCAN_ITEMS;
+        float* wx = st.x[warp];
+
+        float r[SCAN_ITEMS];
+        uint32_t tm[SCAN_ITEMS / 4];
+        if (full_tile) {
+#pragma unroll
+            for (int q = 0; q < SCAN_ITEMS / 4; ++q) {
+                const float4 v = *reinterpret_cast<const float4*>(wx + sx_off(lane, q));
+                r[4 * q + 0] = v.x; r[4 * q + 1] = v.y; r[4 * q + 2] = v.z; r[4 * q + 3] = v.w;
+            }
+            const uint4 tv = *reinterpret_cast<const uint4*>(&st.t[tid * SCAN_ITEMS]);
+            tm[0] = tv.x; tm[1] = tv.y; tm[2] = tv.z; tm[3] = tv.w;
+        } else {
+#pragma unroll
+            for (int q = 0; q < SCAN_ITEMS / 4; ++q) tm[q] = 0;
+#pragma unroll
+            for (int i = 0; i < SCAN_ITEMS; ++i) {
+                const int64_t idx = base + i;
+                const bool in = idx < n;
+                r[i] = in ? rew[idx] : 0.0f;
+                const uint32_t tb = in ? (term[idx] != 0) : 1u;   // padding behaves like an episode end
+                tm[i >> 2] |= tb << (8 * (i & 3));
+            }
+        }
+        auto is_term = [&](int i) -> bool { return ((tm[i >> 2] >> (8 * (i & 3))) & 0xffu) != 0; };
+
+        // 0. look-ahead (warp 0): the 128 transitions right of the tile, composed into one map.  With episodic
+        //    data an episode end almost always lies inside it (A == 0), so the tile's incoming carry is known
+        //    without waiting for any other CTA; only tiles inside very long episodes use the look-back below.
+        if (warp == 0) {
+            const int64_t e0 = tile_base + SCAN_TILE + 4 * lane;
+            Map lk{1.0, 0.0};
+            float lr[4]; bool lt[4];
+            if (full_tile && e0 + 4 <= n) {
+                const float4 v = *reinterpret_cast<const float4*>(&st.lx[4 * lane]);
+                const uint32_t tb = *reinterpret_cast<const uint32_t*>(&st.lt[4 * lane]);
+                lr[0] = v.x; lr[1] = v.y; lr[2] = v.z; lr[3] = v.w;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) lt[j] = ((tb >> (8 * j)) & 0xffu) != 0;
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const bool in = e0 + j < n;
+                    lr[j] = in ? rew[e0 + j] : 0.0f;
+                    lt[j] = in ? (term[e0 + j] != 0) : true;
+                }
+            }
+#pragma unroll
+            for (int j = 3; j >= 0; --j) {
+                const double a = lt[j] ? 0.0 : g;
+                lk.B = __dadd_rn((double)lr[j], __dmul_rn(a, lk.B));
+                lk.A = a * lk.A;
+            }
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                Map o;
+                o.A = __shfl_down_sync(0xffffffffu, lk.A, d);
+                o.B = __shfl_down_sync(0xffffffffu, lk.B, d);
+                if (lane + d < 32) lk = compose(lk, o);
+            }
+            if (lane == 0) { s_lookA = lk.A; s_lookB = lk.B; }
+        }
+
+        // 1. per-thread aggregate map, right to left (B is the serial recurrence with zero carry).  The 16 items
+        //    are two independent chains of 8 (instruction-level parallelism for the dependent fp64 mul/add
+        //    pairs), combined as left(right(c)).
+        constexpr int HALF = SCAN_ITEMS / 2;
+        double Bh = 0.0, Bl = 0.0;
+        bool th = false, tl = false;
+#pragma unroll
+        for (int i = HALF - 1; i >= 0; --i) {
+            const bool t_hi = is_term(i + HALF), t_lo = is_term(i);
+            th |= t_hi; tl |= t_lo;
+            Bh = __dadd_rn((double)r[i + HALF], __dmul_rn(t_hi ? 0.0 : g, Bh));
+            Bl = __dadd_rn((double)r[i], __dmul_rn(t_lo ? 0.0 : g, Bl));
+        }
+        const double Ah = th ? 0.0 : g8, Al = tl ? 0.0 : g8;
+        Map me;
+        me.A = Al * Ah;
+        me.B = __dadd_rn(Bl, __dmul_rn(Al, Bh));
+
+        // 2. reverse inclusive scan over the lanes of the warp (lane l: lanes l..31)
+        Map inc = me;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            Map o;
+            o.A = __shfl_down_sync(0xffffffffu, inc.A, d);
+            o.B = __shfl_down_sync(0xffffffffu, inc.B, d);
+            if (lane + d < 32) inc = compose(inc, o);
+        }
+        Map lane_excl;  // lanes l+1..31
+        lane_excl.A = __shfl_down_sync(0xffffffffu, inc.A, 1);
+        lane_excl.B = __shfl_down_sync(0xffffffffu, inc.B, 1);
+        if (lane == 31) { lane_excl.A = 1.0; lane_excl.B = 0.0; }
+        if (lane == 0) { sA[warp] = inc.A; sB[warp] = inc.B; }
+        __syncthreads();
+
+        // 3. maps of the warps to the right of this one (warp+1 .. last)
+        Map warp_excl{1.0, 0.0};
+        for (int k = NW - 1; k > warp; --k) warp_excl = compose(Map{sA[k], sB[k]}, warp_excl);
+
+        // 4. incoming carry of the tile.  Common case (episodic data): the look-ahead window contains an episode
+        //    end, every thread reads the carry from shared memory and no second barrier is needed; thread 0
+        //    publishes the tile's inclusive value off the critical path.  Otherwise (CTA-uniform branch) thread 0
+        //    runs the decoupled look-back and the CTA waits for it.
+        const bool look_hit = (s_lookA == 0.0) && !(dbg & 8);
+        if (tid == 0) {
+            const Map tile = compose(Map{sA[0], sB[0]}, warp_excl);
+            double carry = 0.0;
+            if (tile.A == 0.0) {       // an episode ends inside the tile: its inclusive value needs no carry
+                sc.incl[t] = tile.B;
+                st_release_i32(sc.flags + t, 2);
+            }
+            if (look_hit) {
+                carry = s_lookB;       // the value of the recurrence at the first transition right of the tile
+            } else if (t > 0) {
+                // decoupled look-back over the tiles to the right: lower tile ids, i.e. earlier iterations of
+                // co-resident CTAs (or lower block ids in the same iteration), which never wait on this one
+                if (tile.A != 0.0) {
+                    sc.aggA[t] = tile.A; sc.aggB[t] = tile.B;
+                    st_release_i32(sc.flags + t, 1);
+                }
+                Map cur{1.0, 0.0};
+                int j = t - 1;
+                while (!(dbg & 1)) {
+                    int f;
+                    while ((f = ld_acquire_i32(sc.flags + j)) == 0) { __nanosleep(20); }
+                    if (f == 2) { carry = __dadd_rn(cur.B, __dmul_rn(cur.A, __ldcg(sc.incl + j))); break; }
+                    cur = compose(cur, Map{__ldcg(sc.aggA + j), __ldcg(sc.aggB + j)});
+                    if (cur.A == 0.0) { carry = cur.B; break; }
+                    --j;   // j >= 0 always holds: tile 0 publishes an inclusive value
+                }
             }
             if (tile.A != 0.0) {
                 sc.incl[t] = __dadd_rn(tile.B, __dmul_rn(tile.A, carry));
-                __threadfence();
                 st_release_i32(sc.flags + t, 2);
             }
+            if (!look_hit) s_carry = carry;
         }
-        s_carry = carry;
-    }
-    __syncthreads();
+        if (!look_hit) __syncthreads();
 
-    // 5. thread's incoming carry, then the reference's serial recurrence over its 16 items
-    double c = s_carry;
-    c = __dadd_rn(warp_excl.B, __dmul_rn(warp_excl.A, c));
-    c = __dadd_rn(lane_excl.B, __dmul_rn(lane_excl.A, c));
-    double lsum = 0.0, lsq = 0.0;
-    if (F32CARRY) {
-        float gf = (float)g;
-        float v = (float)c;
+        // 5. thread's incoming carry, then the reference's serial recurrence over its 16 items
+        double c = look_hit ? s_lookB : s_carry;
+        c = __dadd_rn(warp_excl.B, __dmul_rn(warp_excl.A, c));
+        c = __dadd_rn(lane_excl.B, __dmul_rn(lane_excl.A, c));
+        // the left half starts from the value at item 8 = right-half map applied to the carry
+        const double c_lo = __dadd_rn(Bh, __dmul_rn(Ah, c));
+        if (F32CARRY) {
+            const float gf = (float)g;
+            float vh = (float)c, vl = (float)c_lo;
 #pragma unroll
-        for (int i = SCAN_ITEMS - 1; i >= 0; --i) {
-            if (is_term(i)) v = 0.0f;
-            v = __fadd_rn(r[i], __fmul_rn(gf, v));
-            r[i] = v;
+            for (int i = HALF - 1; i >= 0; --i) {
+                if (is_term(i + HALF)) vh = 0.0f;
+                if (is_term(i)) vl = 0.0f;
+                vh = __fadd_rn(r[i + HALF], __fmul_rn(gf, vh));
+                vl = __fadd_rn(r[i], __fmul_rn(gf, vl));
+                r[i + HALF] = vh;
+                r[i] = vl;
+            }
+        } else {
+            double vh = c, vl = c_lo;
+#pragma unroll
+            for (int i = HALF - 1; i >= 0; --i) {
+                if (is_term(i + HALF)) vh = 0.0;
+                if (is_term(i)) vl = 0.0;
+                vh = __dadd_rn((double)r[i + HALF], __dmul_rn(g, vh));
+                vl = __dadd_rn((double)r[i], __dmul_rn(g, vl));
+                r[i + HALF] = (float)vh;
+                r[i] = (float)vl;
+            }
         }
-    } else {
-        double v = c;
+        float lsum = 0.0f, lsq = 0.0f;
+        if (full_tile) {
+            // back through the (now free) stage for coalesced 128-bit stores
 #pragma unroll
-        for (int i = SCAN_ITEMS - 1; i >= 0; --i) {
-            if (is_term(i)) v = 0.0;
-            v = __dadd_rn((double)r[i], __dmul_rn(g, v));
-            r[i] = (float)v;
+            for (int q = 0; q < SCAN_ITEMS / 4; ++q)
+                *reinterpret_cast<float4*>(wx + sx_off(lane, q)) = make_float4(r[4 * q], r[4 * q + 1], r[4 * q + 2], r[4 * q + 3]);
+#pragma unroll
+            for (int i = 0; i < SCAN_ITEMS; ++i) { lsum += r[i]; lsq = fmaf(r[i], r[i], lsq); }
+            __syncwarp();
+            float4* op = reinterpret_cast<float4*>(out + tile_base + (int64_t)warp * (32 * SCAN_ITEMS));
+#pragma unroll
+            for (int q = 0; q < SCAN_ITEMS / 4; ++q)
+                __stcs(op + q * 32 + lane, *reinterpret_cast<const float4*>(wx + sx_off(q * 8 + (lane >> 2), lane & 3)));
+            __syncwarp();
+        } else {
+#pragma unroll
+            for (int i = 0; i < SCAN_ITEMS; ++i) {
+                if (base + i < n) { out[base + i] = r[i]; lsum += r[i]; lsq = fmaf(r[i], r[i], lsq); }
+            }
         }
-    }
-    if (base + SCAN_ITEMS <= n) {
-        float4* op = reinterpret_cast<float4*>(rew + base);
-#pragma unroll
-        for (int q = 0; q < SCAN_ITEMS / 4; ++q) {
-            op[q] = make_float4(r[4 * q], r[4 * q + 1], r[4 * q + 2], r[4 * q + 3]);
-        }
-#pragma unroll
-        for (int i = 0; i < SCAN_ITEMS; ++i) { double x = r[i]; lsum += x; lsq += x * x; }
-    } else {
-#pragma unroll
-        for (int i = 0; i < SCAN_ITEMS; ++i) {
-            if (base + i < n) { rew[base + i] = r[i]; double x = r[i]; lsum += x; lsq += x * x; }
-        }
-    }
 
-    // 6. K2 statistics of the returns in this tile (fixed-order reduction => deterministic)
+        // 6. K2 statistics of the returns: one {sum, sumsq} pair per warp (fp32 partials over 16 values per
+        //    thread, Float64 from there on, folded in a fixed order by norm_finalize_kernel => deterministic)
+        if (!(dbg & 4)) {
+            double dsum = (double)lsum, dsq = (double)lsq;
 #pragma unroll
-    for (int d = 16; d > 0; d >>= 1) {
-        lsum += __shfl_down_sync(0xffffffffu, lsum, d);
-        lsq += __shfl_down_sync(0xffffffffu, lsq, d);
-    }
-    if (lane == 0) { s_sum[warp] = lsum; s_sq[warp] = lsq; }
-    __syncthreads();
-    if (tid == 0) {
-        double a = 0.0, b = 0.0;
-        for (int k = 0; k < NW; ++k) { a += s_sum[k]; b += s_sq[k]; }
-        tile_stats[2 * (int64_t)tile_idx] = a;
-        tile_stats[2 * (int64_t)tile_idx + 1] = b;
+            for (int d = 16; d > 0; d >>= 1) {
+                dsum += __shfl_down_sync(0xffffffffu, dsum, d);
+                dsq += __shfl_down_sync(0xffffffffu, dsq, d);
+            }
+            if (lane == 0) {
+                tile_stats[2 * ((int64_t)tile_idx * NW + warp)] = dsum;
+                tile_stats[2 * ((int64_t)tile_idx * NW + warp) + 1] = dsq;
+            }
+        }
     }
 }
 
@@ -254,19 +390,36 @@ size_t scan_scratch_bytes(int64_t n) {
     return 16 + (size_t)round_up(tiles * 4, 16) + (size_t)tiles * 3 * sizeof(double);
 }
 
-int launch_returns_scan(ppo_ctx* ctx, float* reward_inout, const uint8_t* terminal, int64_t n,
+int g_scan_dbg = 0;
+int launch_returns_scan(ppo_ctx* ctx, const float* reward_in, float* returns_out, const uint8_t* terminal, int64_t n,
                         double discount, int discount_is_f32, double* tile_stats, void* scratch) {
+    PPO_REQUIRE(reward_in != returns_out, "returns scan runs out of place (the look-ahead reads its right neighbours' rewards)");
     if (n <= 0) return PPO_OK;
     int64_t tiles = ceil_div(n, SCAN_TILE);
     PPO_REQUIRE(tiles < (int64_t)1 << 30, "returns scan: too many tiles");
     ScanScratch sc = carve(scratch, tiles);
     PPO_CUDA(cudaMemsetAsync(scratch, 0, 16 + (size_t)round_up(tiles * 4, 16), ctx->stream));
+    const double g = discount_is_f32 ? (double)(float)discount : discount;
+    double g8 = 1.0;
+    for (int i = 0; i < SCAN_ITEMS / 2; ++i) g8 *= g;  // the same left-to-right product a per-item loop would form
+    // persistent grid: every CTA must be co-resident (the look-back waits on lower tile ids)
+    const size_t smem = 2 * sizeof(ScanStage);
+    int occ = 0;
+    if (discount_is_f32) {
+        PPO_CUDA(cudaFuncSetAttribute(returns_scan_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        PPO_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, returns_scan_kernel<true>, SCAN_THREADS, smem));
+    } else {
+        PPO_CUDA(cudaFuncSetAttribute(returns_scan_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        PPO_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, returns_scan_kernel<false>, SCAN_THREADS, smem));
+    }
+    PPO_REQUIRE(occ >= 1, "returns scan: kernel does not fit on an SM");
+    const int64_t grid = std::min<int64_t>(tiles, (int64_t)ctx->num_sms * occ);
     if (discount_is_f32)
-        returns_scan_kernel<true><<<(unsigned)tiles, SCAN_THREADS, 0, ctx->stream>>>(
-            reward_inout, terminal, n, (double)(float)discount, (int)tiles, sc, tile_stats);
+        returns_scan_kernel<true><<<(unsigned)grid, SCAN_THREADS, smem, ctx->stream>>>(
+            reward_in, returns_out, terminal, n, g, g8, (int)tiles, sc, tile_stats, g_scan_dbg);
     else
-        returns_scan_kernel<false><<<(unsigned)tiles, SCAN_THREADS, 0, ctx->stream>>>(
-            reward_inout, terminal, n, discount, (int)tiles, sc, tile_stats);
+        returns_scan_kernel<false><<<(unsigned)grid, SCAN_THREADS, smem, ctx->stream>>>(
+            reward_in, returns_out, terminal, n, g, g8, (int)tiles, sc, tile_stats, g_scan_dbg);
     ctx->launches += 1;
     PPO_CUDA(cudaGetLastError());
     return PPO_OK;
