@@ -238,12 +238,18 @@ loss_finalize_kernel(const double* __restrict__ partials, int64_t blocks, double
 }
 
 struct Cfg { int G, V; };
+// A = 4 G V floats per sample: G lanes (a power of two <= 32) x V float4 per lane.  Prefer few lanes with several
+// float4 each: the per-sample work (three shuffle reductions, the clip/ratio tail in Float64) is then shared by
+// fewer lanes, which is what bounds the kernel at small A.
 inline bool pick_cfg(int A, Cfg& c) {
     if (A % 4 != 0) return false;
-    int q = A / 4;
-    if (q <= 32) { if ((q & (q - 1)) != 0) return false; c.G = q; c.V = 1; return true; }
-    if (q % 32 != 0 || q / 32 > 4) return false;
-    c.G = 32; c.V = q / 32; return true;
+    const int q = A / 4;
+    for (int V = 4; V >= 1; --V) {
+        if (q % V) continue;
+        const int G = q / V;
+        if (G <= 32 && (G & (G - 1)) == 0) { c.G = G; c.V = V; return true; }
+    }
+    return false;
 }
 
 }  // namespace
@@ -275,9 +281,10 @@ int launch_loss(ppo_ctx* ctx, const float* logits, const float* mask, const int*
     if (pick_cfg(A, c) && aligned) {
 #define PPO_LOSS_CASE(G_, V_) \
     if (c.G == G_ && c.V == V_) loss_vec_kernel<G_, V_><<<(unsigned)blocks, LOSS_THREADS, 0, ctx->stream>>>(a)
-        PPO_LOSS_CASE(1, 1); PPO_LOSS_CASE(2, 1); PPO_LOSS_CASE(4, 1); PPO_LOSS_CASE(8, 1);
-        PPO_LOSS_CASE(16, 1); PPO_LOSS_CASE(32, 1); PPO_LOSS_CASE(32, 2); PPO_LOSS_CASE(32, 3);
-        PPO_LOSS_CASE(32, 4);
+        PPO_LOSS_CASE(1, 1); PPO_LOSS_CASE(1, 2); PPO_LOSS_CASE(1, 3); PPO_LOSS_CASE(1, 4);
+        PPO_LOSS_CASE(2, 3); PPO_LOSS_CASE(2, 4); PPO_LOSS_CASE(4, 3); PPO_LOSS_CASE(4, 4);
+        PPO_LOSS_CASE(8, 3); PPO_LOSS_CASE(8, 4); PPO_LOSS_CASE(16, 3); PPO_LOSS_CASE(16, 4);
+        PPO_LOSS_CASE(32, 3); PPO_LOSS_CASE(32, 4);
 #undef PPO_LOSS_CASE
     } else {
         loss_generic_kernel<<<(unsigned)blocks, LOSS_THREADS, 0, ctx->stream>>>(a);
