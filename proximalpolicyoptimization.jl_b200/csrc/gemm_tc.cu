@@ -323,6 +323,14 @@ tc_gemm_kk_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
             float s[CPT];
 #pragma unroll
             for (int j = 0; j < CPT; ++j) s[j] = 0.0f;
+            if (p.epi == TC_EPI_DGRAD && row < p.M) {
+                // the gate values (this thread's CPT columns of the activation) are needed only after the whole
+                // contraction: pull their lines towards the SM now so that the epilogue does not stall the MMA issuer
+                const char* gp = reinterpret_cast<const char*>(p.gate + (size_t)row * p.N + n0 + half * CPT);
+#pragma unroll
+                for (int l = 0; l < CPT * 4 / 128; ++l)
+                    if (n0 + half * CPT + l * 32 < p.N) asm volatile("prefetch.global.L2 [%0];" ::"l"(gp + l * 128));
+            }
             for (int ch = 0; ch < chunks_per_tile; ++ch, ++cc) {
                 const int acc = (int)(cc & 1u);
                 mbar_wait(tfull + acc, (cc >> 1) & 1u);
