@@ -130,6 +130,19 @@ int ppo_gather_device(ppo_buf* buf, int64_t start, int64_t count, int variant);
 int ppo_batch_read(ppo_buf* buf, int64_t count, float* feat_out, float* mask_out, int64_t* action_out,
                    float* prob_out, float* returns_out);
 
+/* ---- disk replay: src/dataset.jl, src/rollouts_to_disk.jl ------------------ */
+/* DiskDataset(root_directory, trajectory_filename, states_dirname) (src/dataset.jl:1-20) followed by load_sample
+ * (:31-52) for every row, bulk-loaded into the device buffer: parses <root>/<trajectory.csv> (either schema:
+ * `...,returns` written by write_returns_to_disk, src/rollouts_to_disk.jl:106-132, or `...,rewards,terminal` written
+ * by update!, :34-40) and every <root>/<states>/<sample_names[i]> BSON file (BSON.@save of a StateData or of a bare
+ * array).  has_returns = 1: the value column already holds returns; 0: call ppo_compute_returns afterwards. */
+int ppo_disk_dataset_load(ppo_buf* buf, const char* root_directory, const char* trajectory_filename,
+                          const char* states_dirname, int n_threads, int64_t* n_loaded, int* has_returns);
+/* describe the bits-type arrays inside one BSON state file (tests / debugging): eltypes[i][16], counts[i],
+ * ndims[i], dims[i][4] for up to max_arrays arrays, in document order. */
+int ppo_bson_state_arrays(const char* path, int max_arrays, char* eltypes, int64_t* counts, int* ndims,
+                          int64_t* dims, int* n_arrays);
+
 /* ---- policy: test/policy.jl:9-31 (Chain of Dense) ---------------------------------------- */
 /* n_layers Dense layers; dims[0..n_layers] = in, h, ..., out; W[l] = bytes of Julia's
  * Dense.weight [dims[l+1], dims[l]]; hidden activation leakyrelu(slope), last layer linear. */

@@ -15,6 +15,8 @@ from .train import (simplified_ppo_clip, get_linear_action_index, batch_advantag
                     ppo_train_, ppo_iterate_, get_optimizer_learning_rate, ppo_loss_with_entropy_from_logits,
                     format_epoch_line)
 from .evaluate import single_trajectory_return, average_returns
-from . import distributed
+from .rollouts_to_disk import DiskRollouts, write_returns_to_disk, collect_rollouts_disk_
+from .dataset import DiskDataset, load_sample, load_batch, construct_disk_dataset
+from . import distributed, bson_io
 
 GEMM_FP32_SIMT, GEMM_TF32X3_TC, GEMM_BF16_TC = 0, 1, 2

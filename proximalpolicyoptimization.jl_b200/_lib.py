@@ -52,6 +52,8 @@ SIGNATURES = {
     "ppo_gather_indices": (c_int, [vp, PI64, c_i64, PF, PF, PI64, PF, PF]),
     "ppo_gather_device": (c_int, [vp, c_i64, c_i64, c_int]),
     "ppo_batch_read": (c_int, [vp, c_i64, PF, PF, PI64, PF, PF]),
+    "ppo_disk_dataset_load": (c_int, [vp, C.c_char_p, C.c_char_p, C.c_char_p, c_int, PI64, C.POINTER(c_int)]),
+    "ppo_bson_state_arrays": (c_int, [C.c_char_p, c_int, C.c_char_p, PI64, C.POINTER(c_int), PI64, C.POINTER(c_int)]),
     "ppo_policy_create": (c_int, [vp, c_int, C.POINTER(c_int), PPF, PPF, c_flt, C.POINTER(vp)]),
     "ppo_policy_destroy": (c_int, [vp]),
     "ppo_policy_read": (c_int, [vp, PPF, PPF]),

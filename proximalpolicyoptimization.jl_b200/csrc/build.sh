@@ -15,11 +15,13 @@ for src in abi.cu scan.cu shuffle.cu gather.cu loss.cu gemm_simt.cu gemm_tc.cu a
     pids+=($!)
   fi
 done
-obj=build/nccl_dl.o
-if [[ ! -f $obj || nccl_dl.cpp -nt $obj || common.cuh -nt $obj ]]; then
-  ( $NVCC "${FLAGS[@]}" -x cu -c nccl_dl.cpp -o $obj > build/nccl_dl.log 2>&1 || { cat build/nccl_dl.log; exit 1; } ) &
-  pids+=($!)
-fi
+for src in nccl_dl.cpp disk_replay.cpp; do
+  obj=build/${src%.cpp}.o
+  if [[ ! -f $obj || $src -nt $obj || common.cuh -nt $obj || ../../include/ppo_b200.h -nt $obj ]]; then
+    ( $NVCC "${FLAGS[@]}" -x cu -c $src -o $obj > build/${src%.cpp}.log 2>&1 || { cat build/${src%.cpp}.log; exit 1; } ) &
+    pids+=($!)
+  fi
+done
 for p in "${pids[@]:-}"; do [[ -n "$p" ]] && wait "$p"; done
-$NVCC -shared -o "$OUT" build/*.o -lcudart -lcuda -ldl
+$NVCC -gencode arch=compute_100a,code=sm_100a -shared -o "$OUT" build/*.o -lcudart -ldl -lpthread
 echo "built $(realpath $OUT)"

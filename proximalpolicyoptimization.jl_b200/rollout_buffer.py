@@ -32,7 +32,10 @@ class StateData:
 
 
 def batch_state(state_data_vector):
-    """``PPO.batch_state`` — test/quad_game_utilities.jl:26-33 (cat dims=3 / dims=2)."""
+    """``PPO.batch_state`` — test/quad_game_utilities.jl:26-33 (cat dims=3 / dims=2).  Bare-array states (as in
+    the reference's disk-rollout test) are stacked on a new leading (= Julia trailing) dimension."""
+    if not hasattr(state_data_vector[0], "vertex_score"):
+        return np.stack([np.asarray(s) for s in state_data_vector])
     vs = np.stack([np.asarray(s.vertex_score) for s in state_data_vector])
     am = np.stack([np.asarray(s.action_mask) for s in state_data_vector])
     return StateData(vs, am)
