@@ -7,6 +7,7 @@
 // There is deliberately no CPU fallback anywhere in this file: every numeric result comes from a
 // kernel launched on ctx->stream.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -203,7 +204,7 @@ int policy_backward(ppo_policy* p, const float* X, int64_t M) {
 // One minibatch of the update on device-resident batch arrays.  Writes {ppoloss, entropyloss}
 // (unweighted) to p->d_loss_hist[2*slot..].
 int step_core(ppo_policy* p, ppo_opt* opt, const ppo_batch& bt, int64_t nb, int nhe, double epsilon,
-              double entropy_weight, double inv_nb_global, int64_t slot) {
+              double entropy_weight, double inv_nb_global, int64_t slot, const int* d_step = nullptr) {
     ppo_ctx* ctx = p->ctx;
     const int L = p->L;
     const int apa = p->dims[L];
@@ -213,7 +214,8 @@ int step_core(ppo_policy* p, ppo_opt* opt, const ppo_batch& bt, int64_t nb, int 
     PPO_TRY(ensure_loss_buffers(p, nb, A, slot + 1));
     PPO_TRY(policy_forward(p, bt.feat, M));
     PPO_TRY(launch_loss(ctx, p->act[L], bt.mask, bt.action, bt.old_prob, bt.adv, nb, A, epsilon, entropy_weight,
-                        inv_nb_global, p->dlogits, p->d_loss_partials, p->d_loss_hist + 2 * slot, nullptr));
+                        inv_nb_global, p->dlogits, p->d_loss_partials, p->d_loss_hist + (d_step ? 0 : 2 * slot), nullptr,
+                        d_step));
     PPO_TRY(policy_backward(p, bt.feat, M));
     if (ctx->nccl_comm != nullptr && ctx->nranks > 1) PPO_TRY(nccl_allreduce_f32(ctx, p->grads, p->P));
     if (opt != nullptr) {
@@ -224,8 +226,10 @@ int step_core(ppo_policy* p, ppo_opt* opt, const ppo_batch& bt, int64_t nb, int 
     return PPO_OK;
 }
 
-int gather_into(ppo_buf* buf, ppo_batch& bt, const int* d_index, int64_t count, int variant) {
+int gather_into(ppo_buf* buf, ppo_batch& bt, const int* d_index, int64_t count, int variant,
+                const int* d_step = nullptr, int64_t step_stride = 0) {
     GatherArgs a{};
+    a.step = d_step; a.step_stride = step_stride;
     a.feat = buf->feat; a.mask = buf->mask; a.action = buf->action; a.old_prob = buf->old_prob; a.ret = buf->reward;
     a.index = d_index; a.count = count; a.feat_elems = buf->nf * buf->nhe; a.mask_elems = buf->A;
     a.feat_out = bt.feat; a.mask_out = bt.mask; a.action_out = bt.action; a.prob_out = bt.old_prob;
@@ -322,6 +326,8 @@ int ppo_ctx_create(int device, ppo_ctx** out) {
     c->num_sms = prop.multiProcessorCount;
     PPO_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     PPO_CUDA(cudaMallocHost((void**)&c->h_pinned, sizeof(double) * ppo_ctx::PINNED_DOUBLES));
+    PPO_CUDA(cudaMalloc((void**)&c->d_step, sizeof(int)));
+    PPO_CUDA(cudaMemset(c->d_step, 0, sizeof(int)));
     *out = c;
     return PPO_OK;
 }
@@ -333,6 +339,7 @@ int ppo_ctx_destroy(ppo_ctx* ctx) {
     nccl_destroy(ctx);
     if (ctx->d_scratch) cudaFree(ctx->d_scratch);
     if (ctx->d_flush) cudaFree(ctx->d_flush);
+    if (ctx->d_step) cudaFree(ctx->d_step);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -957,12 +964,54 @@ int ppo_step_epoch(ppo_policy* p, ppo_opt* opt, ppo_buf* buf, double epsilon, in
     }
     PPO_TRY(ensure_batch(ctx, buf->batch, batch_size, buf->nf * buf->nhe, buf->A));
     PPO_TRY(ensure_loss_buffers(p, batch_size, buf->A, nbatches));
-    for (int64_t k = 0; k < nbatches; ++k) {
+    auto run_batch = [&](int64_t k) -> int {
         const int64_t start = k * batch_size;
         const int64_t count = std::min(batch_size, num_data - start);
         PPO_TRY(gather_into(buf, buf->batch, buf->perm + start, count, 0));
-        PPO_TRY(step_core(p, opt, buf->batch, count, buf->nhe, epsilon, entropy_weight, 1.0 / counts[(size_t)k], k));
+        return step_core(p, opt, buf->batch, count, buf->nhe, epsilon, entropy_weight, 1.0 / counts[(size_t)k], k);
+    };
+    // All full minibatches of an epoch launch the same ~40 kernels with the same arguments except for the minibatch
+    // number, so the loop body is captured ONCE into a CUDA graph that reads the minibatch number from a device
+    // counter, and replayed: one graph launch per minibatch instead of ~40 kernel launches + ~20 host-side tensor
+    // map encodings.  This is what bounds the small-minibatch regime (the reference's batch_size = 32).  The first
+    // minibatch runs un-captured (it sizes every workspace); the ragged last minibatch too.
+    const int64_t n_full = num_data / batch_size;
+    bool same_global = true;
+    for (int64_t k = 1; k < n_full; ++k) same_global = same_global && counts[(size_t)k] == counts[0];
+    const char* no_graph = getenv("PPO_B200_NO_GRAPH");
+    const bool use_graph = n_full >= 4 && same_global && !(no_graph && no_graph[0] == '1');
+    PPO_TRY(run_batch(0));
+    int64_t k = 1;
+    if (use_graph) {
+        const int one = 1;
+        PPO_CUDA(cudaMemcpyAsync(ctx->d_step, &one, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+        cudaGraph_t graph = nullptr;
+        cudaGraphExec_t exec = nullptr;
+        const int64_t launches_before = ctx->launches;
+        PPO_CUDA(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+        int st = gather_into(buf, buf->batch, buf->perm, batch_size, 0, ctx->d_step, batch_size);
+        if (st == PPO_OK)
+            st = step_core(p, opt, buf->batch, batch_size, buf->nhe, epsilon, entropy_weight, 1.0 / counts[0], 0, ctx->d_step);
+        if (st == PPO_OK) st = launch_step_advance(ctx, ctx->d_step);
+        cudaError_t ce = cudaStreamEndCapture(ctx->stream, &graph);
+        if (st != PPO_OK) { if (graph) cudaGraphDestroy(graph); return st; }
+        PPO_CUDA(ce);
+        PPO_CUDA(cudaGraphInstantiate(&exec, graph, 0));
+        for (; k < n_full; ++k) {
+            cudaError_t le = cudaGraphLaunch(exec, ctx->stream);
+            if (le != cudaSuccess) {
+                cudaGraphExecDestroy(exec); cudaGraphDestroy(graph);
+                PPO_CUDA(le);
+            }
+        }
+        // kernels executed = captured kernel nodes x replays (the capture itself executed nothing)
+        const int64_t nodes = ctx->launches - launches_before;
+        ctx->launches = launches_before + nodes * (n_full - 1);
+        PPO_CUDA(cudaStreamSynchronize(ctx->stream));
+        cudaGraphExecDestroy(exec);
+        cudaGraphDestroy(graph);
     }
+    for (; k < nbatches; ++k) PPO_TRY(run_batch(k));
     if (dp) PPO_TRY(nccl_allreduce_f64(ctx, p->d_loss_hist, 2 * nbatches));
     PPO_TRY(d2h(ctx, ctx->h_pinned, p->d_loss_hist, (size_t)nbatches * 16));
     PPO_CUDA(cudaStreamSynchronize(ctx->stream));

@@ -58,6 +58,7 @@ struct ppo_ctx {
     void* d_flush = nullptr;
     size_t flush_bytes = 0;
     // NCCL (loaded with dlopen on first use)
+    int* d_step = nullptr;           // device-side minibatch counter (CUDA-graph replay of the epoch loop)
     void* nccl_comm = nullptr;
     int nranks = 1, rank = 0;
     static constexpr int PINNED_DOUBLES = 1 << 16;
@@ -164,6 +165,8 @@ struct GatherArgs {
     int64_t count; int feat_elems; int mask_elems;
     float* feat_out; float* mask_out; int* action_out; float* prob_out; float* adv_out;
     const float* norm;         // {mean, inv_std} or nullptr
+    const int* step;           // optional device scalar: index += (*step) * step_stride (CUDA-graph replay)
+    int64_t step_stride;
 };
 int launch_gather(ppo_ctx* ctx, const GatherArgs& a, int variant);
 int launch_permute_inplace_u8(ppo_ctx* ctx, const uint8_t* src, uint8_t* dst, const int* idx, int64_t n);
@@ -172,13 +175,15 @@ int launch_convert_actions_out(ppo_ctx* ctx, const int* a0, int64_t* a1, int64_t
 int launch_linear_index_in(ppo_ctx* ctx, const int64_t* lin1, int* a0, int64_t n, int A, int* d_bad);
 int launch_i64_to_f32(ppo_ctx* ctx, const int64_t* src, float* dst, int64_t n);
 int launch_normalize_bool(ppo_ctx* ctx, uint8_t* t, int64_t n);
+int launch_step_advance(ppo_ctx* ctx, int* d_step);
 
 // loss.cu (K6)
 int64_t loss_num_blocks(int64_t nb, int A);
 int launch_loss(ppo_ctx* ctx, const float* logits, const float* mask, const int* action,
                 const float* old_prob, const float* adv, int64_t nb, int A, double epsilon,
                 double entropy_weight, double inv_nb_global, float* dlogits, double* partials,
-                double* loss_out2 /* {ppoloss, entropyloss unweighted} */, float* probs_out);
+                double* loss_out2 /* {ppoloss, entropyloss unweighted} */, float* probs_out,
+                const int* step = nullptr /* optional device scalar: write to loss_out2 + 2 * (*step) */);
 
 // gemm_simt.cu (K5/K7, fp32 reference path) + skinny last layer
 int launch_linear_fwd_simt(ppo_ctx* ctx, const float* X, const float* W, const float* bias, float* Y,

@@ -37,6 +37,7 @@ __device__ __forceinline__ void warp_copy_vec4(const float4* __restrict__ s, flo
 
 __global__ void __launch_bounds__(256)
 gather_rows_vec_kernel(GatherArgs a) {
+    if (a.step != nullptr) a.index += (int64_t)(*a.step) * a.step_stride;   // minibatch number lives on the device (CUDA graph replay)
     const int lane = threadIdx.x & 31;
     const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     const int fvec = a.feat_elems >> 2, mvec = a.mask_elems >> 2;
@@ -51,6 +52,7 @@ gather_rows_vec_kernel(GatherArgs a) {
 
 __global__ void __launch_bounds__(256)
 gather_rows_scalar_kernel(GatherArgs a) {
+    if (a.step != nullptr) a.index += (int64_t)(*a.step) * a.step_stride;
     const int lane = threadIdx.x & 31;
     const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     for (int64_t rec = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; rec < a.count; rec += warps) {
@@ -67,6 +69,7 @@ gather_rows_scalar_kernel(GatherArgs a) {
 // per-sample scalars: one thread per sample, coalesced stores
 __global__ void __launch_bounds__(256)
 gather_scalars_kernel(GatherArgs a) {
+    if (a.step != nullptr) a.index += (int64_t)(*a.step) * a.step_stride;
     float mu = 0.0f, inv = 1.0f;
     if (a.norm != nullptr) { mu = a.norm[0]; inv = a.norm[1]; }
     for (int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; b < a.count;
@@ -135,6 +138,7 @@ constexpr int BULK_MAX_STAGES = 8;
 __global__ void __launch_bounds__(BULK_WARPS * 32)
 gather_rows_bulk_kernel(GatherArgs a, int stages, int rec_bytes_padded) {
     extern __shared__ __align__(128) unsigned char smem[];
+    if (a.step != nullptr) a.index += (int64_t)(*a.step) * a.step_stride;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)BULK_WARPS * stages * rec_bytes_padded);
     unsigned char* my = smem + (size_t)warp * stages * rec_bytes_padded;
@@ -222,6 +226,8 @@ linear_in_kernel(const int64_t* __restrict__ lin1, int* __restrict__ a0, int64_t
         a0[i] = (int)v;
     }
 }
+
+__global__ void step_advance_kernel(int* step) { *step += 1; }
 
 __global__ void __launch_bounds__(256)
 normalize_bool_kernel(uint8_t* __restrict__ t, int64_t n) {
@@ -311,6 +317,13 @@ int launch_convert_actions_out(ppo_ctx* ctx, const int* a0, int64_t* a1, int64_t
 int launch_linear_index_in(ppo_ctx* ctx, const int64_t* lin1, int* a0, int64_t n, int A, int* d_bad) {
     if (n <= 0) return PPO_OK;
     linear_in_kernel<<<grid_for(ctx, n, 256), 256, 0, ctx->stream>>>(lin1, a0, n, A, d_bad);
+    ctx->launches += 1;
+    PPO_CUDA(cudaGetLastError());
+    return PPO_OK;
+}
+
+int launch_step_advance(ppo_ctx* ctx, int* d_step) {
+    step_advance_kernel<<<1, 1, 0, ctx->stream>>>(d_step);
     ctx->launches += 1;
     PPO_CUDA(cudaGetLastError());
     return PPO_OK;

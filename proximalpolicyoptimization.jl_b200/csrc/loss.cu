@@ -224,7 +224,9 @@ loss_generic_kernel(LossArgs a) {
 
 // out[0] = ppoloss = -(1/nb) sum min(gain, clip);  out[1] = entropyloss = -(1/nb) sum H_b
 __global__ void __launch_bounds__(256)
-loss_finalize_kernel(const double* __restrict__ partials, int64_t blocks, double inv_nb, double* __restrict__ out2) {
+loss_finalize_kernel(const double* __restrict__ partials, int64_t blocks, double inv_nb, double* __restrict__ out2,
+                     const int* __restrict__ step) {
+    if (step != nullptr) out2 += 2 * (int64_t)(*step);
     __shared__ double s1[256], s2[256];
     double a = 0.0, b = 0.0;
     for (int64_t i = threadIdx.x; i < blocks; i += 256) { a += partials[2 * i]; b += partials[2 * i + 1]; }
@@ -264,7 +266,7 @@ int64_t loss_num_blocks(int64_t nb, int A) {
 
 int launch_loss(ppo_ctx* ctx, const float* logits, const float* mask, const int* action, const float* old_prob,
                 const float* adv, int64_t nb, int A, double epsilon, double entropy_weight, double inv_nb_global,
-                float* dlogits, double* partials, double* loss_out2, float* probs_out) {
+                float* dlogits, double* partials, double* loss_out2, float* probs_out, const int* step) {
     PPO_REQUIRE(nb >= 1 && A >= 1, "loss: nb=%lld A=%d", (long long)nb, A);
     LossArgs a;
     a.logits = logits; a.mask = mask; a.action = action; a.old_prob = old_prob; a.adv = adv;
@@ -291,7 +293,7 @@ int launch_loss(ppo_ctx* ctx, const float* logits, const float* mask, const int*
     }
     ctx->launches += 1;
     PPO_CUDA(cudaGetLastError());
-    loss_finalize_kernel<<<1, 256, 0, ctx->stream>>>(partials, blocks, inv_nb_global, loss_out2);
+    loss_finalize_kernel<<<1, 256, 0, ctx->stream>>>(partials, blocks, inv_nb_global, loss_out2, step);
     ctx->launches += 1;
     PPO_CUDA(cudaGetLastError());
     return PPO_OK;

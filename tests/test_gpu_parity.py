@@ -403,3 +403,26 @@ def test_error_behaviour(ctx):
     with pytest.raises(TypeError):
         ds["x"]
     buf.close()
+
+
+def test_cuda_graph_epoch_is_bit_identical(ctx, monkeypatch):
+    # the epoch loop replayed from a CUDA graph (device-side minibatch counter) vs plain launches
+    cfg = S.CONFIGS["t1"]
+    data = S.make_buffer(cfg)
+    W, b = S.make_weights(cfg)
+    old = S.rng_for(cfg, 7).uniform(0.05, 1.0, cfg.N).astype(np.float32)
+    perm1 = O.feistel_permutation(cfg.N, 5) + 1
+    out = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("PPO_B200_NO_GRAPH", mode)
+        buf = P.DeviceRollouts(cfg.nf, cfg.nhe, cfg.apa, cfg.N, ctx)
+        buf.append(data["feat"], data["mask"], old, data["action"], data["reward"], data["terminal"])
+        P.compute_state_value_(buf, 1.0)
+        pol = P.Policy(cfg.nf, cfg.H, cfg.L, cfg.apa, ctx, weights=W, biases=b)
+        opt = P.Adam(1e-4)
+        losses = [P.step_epoch_(pol, opt, P.construct_dataset(buf), 0.05, 48, 0.01, perm=perm1) for _ in range(2)]
+        Wd, bd = pol.weights()
+        out[mode] = (losses, np.concatenate([w.ravel() for w in Wd] + [x.ravel() for x in bd]))
+        pol.close(); buf.close()
+    assert out["0"][0] == out["1"][0]
+    assert np.array_equal(out["0"][1], out["1"][1])
