@@ -140,14 +140,17 @@ def make_data(cfg, P, S, ctx, W, b, rank, cheap_old=False):
     t0 = time.perf_counter()
     import dataclasses
     cfg_r = dataclasses.replace(cfg, cid=cfg.cid + 100 * rank)     # a different shard per rank
-    raw = S.make_buffer(cfg_r)
     pinned = {}
-    for k, v in raw.items():
-        arr = v.astype(np.uint8) if k == "terminal" else v
-        tt = torch.empty(arr.shape, dtype=torch.from_numpy(arr[:1]).dtype, pin_memory=True)
-        tt.numpy()[...] = arr
-        pinned[k] = tt
-    data = {k: v.numpy() for k, v in pinned.items()}
+
+    def alloc(shape, dtype):
+        tt = torch.empty(shape, dtype=torch.from_numpy(np.empty(1, dtype)).dtype, pin_memory=True)
+        pinned[len(pinned)] = tt          # keep the pinned storage alive
+        return tt.numpy()
+
+    data = S.make_buffer(cfg_r, alloc=alloc)      # generated in place in pinned host memory (no second copy)
+    term = alloc(data["terminal"].shape, np.uint8)
+    term[:] = data["terminal"]
+    data["terminal"] = term
     data["_pins"] = pinned
     sel = np.empty(cfg.N, np.float32)
     if cheap_old:
@@ -165,11 +168,35 @@ def make_data(cfg, P, S, ctx, W, b, rank, cheap_old=False):
     po.numpy()[...] = old
     data["old"] = po.numpy()
     data["_pins"]["old"] = po
+    data["_keep"] = None
     log(f"[rank {rank}] synthetic data ready in {time.perf_counter() - t0:.1f} s")
     return data
 
 
+class _StdoutToStderr:
+    """Route fd 1 to stderr while libraries initialise and run (NCCL prints its version banner on stdout), so that
+    the only thing rank 0 ever writes to stdout is the JSON line."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+
+
 def run_ours(args):
+    with _StdoutToStderr():
+        line = _run_ours(args)
+    if line is not None:
+        print(line, flush=True)
+
+
+def _run_ours(args):
     import torch
     import torch.distributed as dist
     import ppo_b200 as P
@@ -247,12 +274,13 @@ def run_ours(args):
     ms_step, clocks, launches = timed(resident_step, args.steps, args.warmup, "resident")
     value = cfg.N * world / (ms_step * 1e-3)
     if args.profile:
+        line = None
         if rank == 0:
-            print(json.dumps({"profile_only": True, "value": value, "ms_per_step": ms_step, "gpu_launches": launches,
-                              "launches_total": ctx.launch_count()}), flush=True)
+            line = json.dumps({"profile_only": True, "value": value, "ms_per_step": ms_step, "gpu_launches": launches,
+                               "launches_total": ctx.launch_count()})
         barrier()
         pol.close(); buf.close(); ctx.close()
-        return
+        return line
 
     # ---- end-to-end leg: host buffers in, losses out ----------------------------------------------
     def e2e_step(i):
@@ -317,7 +345,8 @@ def run_ours(args):
                     "frac_of_3xtf32_ceiling": round(ach / (pk["bf16_sustained"] / 6.0), 4) if passes == 3 else None,
                     "traffic_source": "ncu --set full, profiles/r01_ncu_summary.md (dram read 4.38 GB + write 4.27 GB per launch)",
                     "detail": dom}
-        cpu = cpu_baseline(cfg, data, W, b)
+        # the CPU baseline is timed at N = 1 only (torchrun pins OMP_NUM_THREADS=1 and the ranks share the host)
+        cpu = cpu_baseline(cfg, data, W, b) if world == 1 else None
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
@@ -333,12 +362,11 @@ def run_ours(args):
             "gpu_launches": launches, "clocks": clocks,
             "loss_last_step": [float(last["loss"][0][0]), float(last["loss"][1][0])],
         }
-    if out is not None:
-        print(json.dumps(out), flush=True)
     barrier()
     pol.close(); buf.close(); ctx.close()
     if world > 1:
         dist.destroy_process_group()
+    return json.dumps(out) if out is not None else None
 
 
 def run_reference(args):

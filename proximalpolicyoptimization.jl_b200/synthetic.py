@@ -104,21 +104,24 @@ def make_actions(rng, mask):
     return (np.argmax(score, axis=1) + 1).astype(np.int64)
 
 
-def make_buffer(cfg: Config, n=None, chunk=65536):
-    """All rollout arrays except the old action probabilities (they need the policy)."""
+def make_buffer(cfg: Config, n=None, chunk=65536, alloc=None):
+    """All rollout arrays except the old action probabilities (they need the policy).  ``alloc(shape, dtype)``
+    optionally provides the output arrays (e.g. pinned host memory) so that large configs are generated in place."""
     n = cfg.N if n is None else n
     rng = rng_for(cfg, 0)
-    feat = np.empty((n, cfg.nhe, cfg.nf), np.float32)
+    alloc = alloc or (lambda shape, dtype: np.empty(shape, dtype))
+    feat = alloc((n, cfg.nhe, cfg.nf), np.float32)
     for s in range(0, n, chunk):
         e = min(n, s + chunk)
         feat[s:e] = rng.integers(-3, 9, size=(e - s, cfg.nhe, cfg.nf), dtype=np.int8)
-    mask = np.empty((n, cfg.A), np.float32)
-    act = np.empty(n, np.int64)
+    mask = alloc((n, cfg.A), np.float32)
+    act = alloc((n,), np.int64)
     for s in range(0, n, chunk):
         e = min(n, s + chunk)
         mask[s:e] = make_masks(rng, e - s, cfg.nhe, cfg.apa)
         act[s:e] = make_actions(rng, mask[s:e])
-    reward = rng.integers(-4, 5, size=n).astype(np.float32)
+    reward = alloc((n,), np.float32)
+    reward[:] = rng.integers(-4, 5, size=n)
     terminal = make_episode_terminals(rng, n, cfg.max_episode)
     return {"feat": feat, "mask": mask, "action": act, "reward": reward, "terminal": terminal}
 
