@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py — PPO-update samples/s on B200 (metric of BASELINE.json), one JSON line on stdout.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--gemm fp32|tf32x3|bf16]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--gemm fp32|tf32x3|f16x3]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 A "step" is one pass of the hot path over one filled rollout buffer: returns scan over the whole
@@ -217,7 +217,7 @@ def _run_ours(args):
     W, b = S.make_weights(cfg)
     data = make_data(cfg, P, S, ctx, W, b, rank, cheap_old=args.profile)
 
-    gemm_mode = {"fp32": P.GEMM_FP32_SIMT, "tf32x3": P.GEMM_TF32X3_TC, "bf16": P.GEMM_BF16_TC}[args.gemm]
+    gemm_mode = {"fp32": P.GEMM_FP32_SIMT, "tf32x3": P.GEMM_TF32X3_TC, "f16x3": P.GEMM_F16X3_TC}[args.gemm]
     pol = P.Policy(cfg.nf, cfg.H, cfg.L, cfg.apa, ctx, weights=W, biases=b)
     pol.set_gemm_mode(gemm_mode)
     opt = P.Optimiser(P.Adam(ETA))
@@ -314,11 +314,12 @@ def _run_ours(args):
         hbm("K4_gather_bulk", "gather1", cfg.N, cfg.nf * cfg.nhe, cfg.A, B_local)
         hbm("K6_loss_namedB", "loss", B_local, cfg.A)
         hbm("K6_loss_1M", "loss", 1 << 20, cfg.A, iters=5)
-        hbm("K5_head_fwd", "head_fwd", M, cfg.H, cfg.apa, iters=5)
-        hbm("K7_head_bwd", "head_bwd", M, cfg.H, cfg.apa, iters=5)
+        hp = "head16" if args.gemm == "f16x3" else "head"     # the fp16-split engine has its own head kernels
+        hbm("K5_head_fwd", hp + "_fwd", M, cfg.H, cfg.apa, iters=5)
+        hbm("K7_head_bwd", hp + "_bwd", M, cfg.H, cfg.apa, iters=5)
         hbm("K1_scan_64M_longepisodes", "scan", 64 * 1024 * 1024, 1 << 30, 1, iters=3)
         hbm("K8_adam", "adam", cfg.num_params)
-        gname = {"fp32": "gemm", "tf32x3": "tc1", "bf16": "tc2"}[args.gemm]
+        gname = {"fp32": "gemm", "tf32x3": "tc1", "f16x3": "tc3"}[args.gemm]
         dom = {}
         for kind in ("fwd", "dgrad", "wgrad"):
             ms, flops = ctx.bench_kernel(f"{gname}_{kind}", M, cfg.H, cfg.H, 0, 3, True)
@@ -333,16 +334,18 @@ def _run_ours(args):
         # bf16 rate, so the ceiling of this scheme is peak / 6.
         fwd = dom["fwd"]
         ach = fwd["tflops_fp32_equiv"]
-        passes = 3 if args.gemm == "tf32x3" else 1
+        passes = 3 if args.gemm in ("tf32x3", "f16x3") else 1
+        # ceiling of the 3-pass split: tf32 runs at half the bf16/fp16 rate (peak / 6); fp16 at the full rate (peak / 3)
+        ceiling = pk["bf16_sustained"] / (6.0 if args.gemm == "tf32x3" else 3.0)
+        kname = {"tf32x3": "tc_gemm_kk_kernel<256>", "f16x3": "f16_gemm_kk_kernel<256>", "fp32": "sgemm_kernel"}[args.gemm]
         roofline = {"bound": "tensor", "achieved": ach, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
                     "frac": round(ach / pk["bf16_sustained"], 4),
                     "traffic": 8.65e9 if (args.gemm == "tf32x3" and M == 1 << 20 and cfg.H == 512) else None,
-                    "kernel": ("tc_gemm_kk_kernel<256>" if args.gemm == "tf32x3" else "sgemm_kernel") +
-                              f" (hidden Dense forward, M={M}, K=N={cfg.H})",
+                    "kernel": kname + f" (hidden Dense forward, M={M}, K=N={cfg.H})",
                     "ms_per_launch": fwd["ms"],
                     "peak_source": pk["src"] + " bf16 sustained (MEASURED_PEAKS.json; kernel timed inside a long step)",
                     "tensor_flops_issued_tflops": round(ach * passes, 2),
-                    "frac_of_3xtf32_ceiling": round(ach / (pk["bf16_sustained"] / 6.0), 4) if passes == 3 else None,
+                    "frac_of_3pass_ceiling": round(ach / ceiling, 4) if passes == 3 else None,
                     "traffic_source": "ncu --set full, profiles/r01_ncu_summary.md (dram read 4.38 GB + write 4.27 GB per launch)",
                     "detail": dom}
         # the CPU baseline is timed at N = 1 only (torchrun pins OMP_NUM_THREADS=1 and the ranks share the host)
@@ -350,7 +353,7 @@ def _run_ours(args):
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": {"fp32": "f32", "tf32x3": "tf32x3", "bf16": "bf16"}[args.gemm],
+            "vs_baseline": None, "dtype": {"fp32": "f32", "tf32x3": "tf32x3", "f16x3": "f16x3"}[args.gemm],
             "data": "synthetic",
             "config": {"workload": cfg.name + (f" x{world} shards" if world > 1 else ""),
                        "transitions_per_gpu": cfg.N, "minibatch_rows_per_gpu": B_local,
@@ -415,7 +418,7 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--gemm", default=os.environ.get("PPO_B200_GEMM", "tf32x3"), choices=["fp32", "tf32x3", "bf16"])
+    ap.add_argument("--gemm", default=os.environ.get("PPO_B200_GEMM", "f16x3"), choices=["fp32", "tf32x3", "f16x3"])
     ap.add_argument("--profile", action="store_true",
                     help="only the warm-up + timed resident steps (for ncu launch lists): no data-generation forward, "
                          "no per-kernel hooks, no CPU baseline")

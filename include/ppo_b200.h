@@ -48,7 +48,9 @@ typedef enum {
 typedef enum {
     PPO_GEMM_FP32_SIMT = 0,   /* fp32 FFMA tiles: bit-for-bit deterministic fp32 reference path */
     PPO_GEMM_TF32X3_TC = 1,   /* tcgen05 kind::tf32, error-compensated 3-pass split: fp32 parity */
-    PPO_GEMM_BF16_TC = 2      /* tcgen05 kind::f16 (bf16 in, fp32 accumulate): fast mode */
+    PPO_GEMM_BF16_TC = 2,     /* tcgen05 kind::f16 (bf16 in, fp32 accumulate): fast mode (declared, not built) */
+    PPO_GEMM_F16X3_TC = 3     /* tcgen05 kind::f16 on power-of-two-scaled fp16 hi/lo pairs, error-compensated 3-pass
+                                 split: fp32 parity at twice the tf32 tensor rate and half the operand bytes */
 } ppo_gemm_mode;
 
 const char* ppo_last_error(void);

@@ -19,4 +19,4 @@ from .rollouts_to_disk import DiskRollouts, write_returns_to_disk, collect_rollo
 from .dataset import DiskDataset, load_sample, load_batch, construct_disk_dataset
 from . import distributed, bson_io
 
-GEMM_FP32_SIMT, GEMM_TF32X3_TC, GEMM_BF16_TC = 0, 1, 2
+GEMM_FP32_SIMT, GEMM_TF32X3_TC, GEMM_BF16_TC, GEMM_F16X3_TC = 0, 1, 2, 3

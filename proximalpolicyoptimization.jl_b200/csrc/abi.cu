@@ -15,6 +15,7 @@
 
 #include "common.cuh"
 #include "gemm_tc.cuh"
+#include "gemm_f16.cuh"
 
 namespace ppo {
 
@@ -144,10 +145,18 @@ int ensure_loss_buffers(ppo_policy* p, int64_t nb, int A, int64_t hist) {
     return PPO_OK;
 }
 
+// rebuild the tensor-core engines' operand copies of the weights (after policy_write / every Adam step)
+int refresh_engine_weights(ppo_policy* p) {
+    if (p->gemm_mode == PPO_GEMM_F16X3_TC) return f16_refresh_weights(p);
+    if (p->gemm_mode != PPO_GEMM_FP32_SIMT) return tc_refresh_weights(p);
+    return PPO_OK;
+}
+
 // forward through all Dense layers: act[l] for l = 1..L  (act[L] = logits, linear)
 int policy_forward(ppo_policy* p, const float* X, int64_t M) {
     ppo_ctx* ctx = p->ctx;
     const int L = p->L;
+    if (p->gemm_mode == PPO_GEMM_F16X3_TC) return f16_forward(p, X, M);
     const float* in = X;
     for (int l = 0; l < L; ++l) {
         const int K = p->dims[l], N = p->dims[l + 1];
@@ -171,6 +180,7 @@ int policy_forward(ppo_policy* p, const float* X, int64_t M) {
 int policy_backward(ppo_policy* p, const float* X, int64_t M) {
     ppo_ctx* ctx = p->ctx;
     const int L = p->L;
+    if (p->gemm_mode == PPO_GEMM_F16X3_TC) return f16_backward(p, M);
     const bool tc = p->gemm_mode != PPO_GEMM_FP32_SIMT;
     const float* delta = p->dlogits;
     int pp = 0;
@@ -221,7 +231,7 @@ int step_core(ppo_policy* p, ppo_opt* opt, const ppo_batch& bt, int64_t nb, int 
     if (opt != nullptr) {
         PPO_TRY(launch_adam(ctx, p->params, opt->m, opt->v, p->grads, p->P, opt->eta, opt->beta1, opt->beta2,
                             opt->eps, opt->d_bp, 1.0f));
-        if (p->gemm_mode != PPO_GEMM_FP32_SIMT) PPO_TRY(tc_refresh_weights(p));
+        PPO_TRY(refresh_engine_weights(p));
     }
     return PPO_OK;
 }
@@ -702,6 +712,7 @@ int ppo_policy_destroy(ppo_policy* p) {
     cudaStreamSynchronize(p->ctx->stream);
     free_workspace(p);
     tc_destroy(p);
+    f16_destroy(p);
     dev_free(p->params); dev_free(p->grads); dev_free(p->d_loss_partials); dev_free(p->d_loss_hist);
     free_batch(p->hbatch);
     delete p;
@@ -730,7 +741,7 @@ int ppo_policy_write(ppo_policy* p, const float* const* W, const float* const* b
         PPO_TRY(h2d(ctx, p->params + p->w_off[l], W[l], (size_t)p->dims[l] * p->dims[l + 1] * 4));
         PPO_TRY(h2d(ctx, p->params + p->b_off[l], b[l], (size_t)p->dims[l + 1] * 4));
     }
-    if (p->gemm_mode != PPO_GEMM_FP32_SIMT) PPO_TRY(tc_refresh_weights(p));
+    PPO_TRY(refresh_engine_weights(p));
     PPO_CUDA(cudaStreamSynchronize(ctx->stream));
     return PPO_OK;
 }
@@ -738,12 +749,12 @@ int ppo_policy_write(ppo_policy* p, const float* const* W, const float* const* b
 int ppo_policy_set_gemm_mode(ppo_policy* p, int mode) {
     PPO_REQUIRE(p != nullptr, "null policy");
     PPO_TRY(use(p->ctx));
-    PPO_REQUIRE(mode == PPO_GEMM_FP32_SIMT || mode == PPO_GEMM_TF32X3_TC || mode == PPO_GEMM_BF16_TC,
-                "set_gemm_mode: unknown mode %d", mode);
-    if (mode != PPO_GEMM_FP32_SIMT) PPO_TRY(tc_prepare(p, mode));
+    PPO_REQUIRE(mode == PPO_GEMM_FP32_SIMT || mode == PPO_GEMM_TF32X3_TC || mode == PPO_GEMM_BF16_TC ||
+                mode == PPO_GEMM_F16X3_TC, "set_gemm_mode: unknown mode %d", mode);
+    if (mode == PPO_GEMM_F16X3_TC) PPO_TRY(f16_prepare(p));
+    else if (mode != PPO_GEMM_FP32_SIMT) PPO_TRY(tc_prepare(p, mode));
     p->gemm_mode = mode;
-    if (mode != PPO_GEMM_FP32_SIMT) PPO_TRY(tc_refresh_weights(p));
-    return PPO_OK;
+    return refresh_engine_weights(p);
 }
 
 int64_t ppo_policy_num_params(ppo_policy* p) { return p ? p->P : -1; }
@@ -830,7 +841,7 @@ int ppo_adam_update(ppo_opt* o, const float* grad_flat) {
     PPO_TRY(use(ctx));
     PPO_TRY(h2d(ctx, p->grads, grad_flat, (size_t)p->P * 4));
     PPO_TRY(launch_adam(ctx, p->params, o->m, o->v, p->grads, p->P, o->eta, o->beta1, o->beta2, o->eps, o->d_bp, 1.0f));
-    if (p->gemm_mode != PPO_GEMM_FP32_SIMT) PPO_TRY(tc_refresh_weights(p));
+    PPO_TRY(refresh_engine_weights(p));
     PPO_CUDA(cudaStreamSynchronize(ctx->stream));
     return PPO_OK;
 }

@@ -1,6 +1,7 @@
 // bench_hooks.cu — ppo_bench_kernel: time ONE kernel of the hot path in isolation on a synthetic,
 // device-resident problem (CUDA events on the ctx stream, optional L2 flush between launches).
 // Used by bench.py for the per-kernel roofline numbers; not part of the reference-facing API.
+#include <math.h>
 #include <string.h>
 
 #include <algorithm>
@@ -8,6 +9,7 @@
 
 #include "common.cuh"
 #include "gemm_tc.cuh"
+#include "gemm_f16.cuh"
 
 namespace ppo {
 extern int g_scan_dbg;
@@ -258,6 +260,60 @@ extern "C" int ppo_bench_kernel(ppo_ctx* ctx, const char* which, int64_t n, int 
         *work_out = 2.0 * (double)M * K * N;
         return PPO_OK;
     }
+    if (w == "tc3_fwd" || w == "tc3_dgrad" || w == "tc3_wgrad" || w == "head16_fwd" || w == "head16_bwd") {
+        // fp16-split engine: operands as scaled fp16 hi/lo pairs (uniform [-1, 1) data; output bound K + 1)
+        const int64_t M = n; const int K = a, N = b;
+        float *X, *W, *bias, *Y, *dW, *db, *part, *sc_, *lg;
+        __half *Xh, *Xl, *Wh, *Wl, *WTh, *WTl, *Yh, *Yl, *dXh, *dXl;
+        unsigned* st;
+        PPO_TRY(sc.alloc(&X, (size_t)std::max<int64_t>(M * K, M * N))); PPO_TRY(sc.alloc(&W, (size_t)K * N));
+        PPO_TRY(sc.alloc(&bias, (size_t)std::max(K, N))); PPO_TRY(sc.alloc(&Y, (size_t)M * N));
+        PPO_TRY(sc.alloc(&Xh, (size_t)M * K + 128)); PPO_TRY(sc.alloc(&Xl, (size_t)M * K + 128));
+        PPO_TRY(sc.alloc(&Wh, (size_t)K * N)); PPO_TRY(sc.alloc(&Wl, (size_t)K * N));
+        PPO_TRY(sc.alloc(&WTh, (size_t)K * N)); PPO_TRY(sc.alloc(&WTl, (size_t)K * N));
+        PPO_TRY(sc.alloc(&Yh, (size_t)M * N + 128)); PPO_TRY(sc.alloc(&Yl, (size_t)M * N + 128));
+        PPO_TRY(sc.alloc(&dXh, (size_t)M * K + 128)); PPO_TRY(sc.alloc(&dXl, (size_t)M * K + 128));
+        PPO_TRY(sc.alloc(&dW, (size_t)K * N)); PPO_TRY(sc.alloc(&db, (size_t)std::max(K, N)));
+        PPO_TRY(sc.alloc(&sc_, 16)); PPO_TRY(sc.alloc(&st, 4)); PPO_TRY(sc.alloc(&lg, (size_t)M * 4));
+        const size_t pb = std::max(f16_test_partial_bytes(ctx, M, K, N), f16_test_head_partial_bytes(M, K, N <= 4 ? N : 4));
+        PPO_TRY(sc.alloc((char**)&part, pb));
+        PPO_CUDA(cudaMemsetAsync(st, 0, 16, ctx->stream));
+        PPO_TRY(fill(ctx, X, M * K, 0, 1, 1)); PPO_TRY(fill(ctx, W, (int64_t)K * N, 0, 1, 2));
+        PPO_TRY(fill(ctx, bias, std::max(K, N), 0, 1, 3)); PPO_TRY(fill(ctx, Y, M * N, 0, 1, 4));
+        float *sX = sc_, *sW = sc_ + 2, *sY = sc_ + 4, *sO = sc_ + 6;
+        PPO_TRY(f16_test_operand(ctx, X, Xh, Xl, M * K, sX, st));
+        PPO_TRY(f16_test_operand(ctx, Y, Yh, Yl, M * N, sY, st));
+        if (w == "head16_fwd" || w == "head16_bwd") {
+            PPO_REQUIRE(N <= 4, "bench head16: N <= 4");
+            PPO_TRY(fill(ctx, lg, M * N, 0, 1, 5));
+            PPO_TRY(f16_test_set_scale(ctx, sO, (float)N + 1.0f));
+            if (w == "head16_fwd") {
+                PPO_TRY(time_loop(ctx, sc, iters, flush_l2_flag,
+                                  [&]() { return f16_test_head_fwd(ctx, Xh, Xl, W, bias, lg, M, K, N, sX); }, ms_out));
+                *work_out = (double)M * (4.0 * K + 4.0 * N);
+            } else {
+                PPO_TRY(time_loop(ctx, sc, iters, flush_l2_flag,
+                                  [&]() { return f16_test_head_bwd(ctx, Xh, Xl, lg, W, dXh, dXl, dW, db, bias, M, K, N, 0.01f, part, pb, sX, sO); }, ms_out));
+                *work_out = (double)M * (8.0 * K + 4.0 * N);
+            }
+            return PPO_OK;
+        }
+        PPO_TRY(f16_test_weight(ctx, W, Wh, Wl, WTh, WTl, K, N, sW, st));
+        if (w == "tc3_fwd") {
+            PPO_TRY(f16_test_set_scale(ctx, sO, (float)K + 1.0f));
+            PPO_TRY(time_loop(ctx, sc, iters, flush_l2_flag,
+                              [&]() { return f16_test_fwd(ctx, Xh, Xl, WTh, WTl, bias, Yh, Yl, M, K, N, 1, 0.01f, sX, sW, sO); }, ms_out));
+        } else if (w == "tc3_dgrad") {
+            PPO_TRY(f16_test_set_scale(ctx, sO, (float)N));
+            PPO_TRY(time_loop(ctx, sc, iters, flush_l2_flag,
+                              [&]() { return f16_test_dgrad(ctx, Yh, Yl, Wh, Wl, Xh, dXh, dXl, M, K, N, 0.01f, part, db, sY, sW, sO); }, ms_out));
+        } else {
+            PPO_TRY(time_loop(ctx, sc, iters, flush_l2_flag,
+                              [&]() { return f16_test_wgrad(ctx, Xh, Xl, Yh, Yl, dW, part, pb, M, K, N, sX, sY); }, ms_out));
+        }
+        *work_out = 2.0 * (double)M * K * N;
+        return PPO_OK;
+    }
     set_error("bench_kernel: unknown kernel '%s'", which);
     return PPO_ERR_INVALID;
 }
@@ -267,7 +323,8 @@ extern "C" int ppo_dense_op(ppo_ctx* ctx, int mode, int op, int64_t M, int K, in
     PPO_REQUIRE(ctx && X && W && out, "dense_op: null argument");
     PPO_REQUIRE(op >= 0 && op <= 2 && M >= 1 && K >= 1 && N >= 1, "dense_op: bad op/shape");
     PPO_REQUIRE(op == 0 || dY != nullptr, "dense_op: dY required");
-    PPO_REQUIRE(mode == PPO_GEMM_FP32_SIMT || mode == PPO_GEMM_TF32X3_TC, "dense_op: unsupported engine %d", mode);
+    PPO_REQUIRE(mode == PPO_GEMM_FP32_SIMT || mode == PPO_GEMM_TF32X3_TC || mode == PPO_GEMM_F16X3_TC,
+                "dense_op: unsupported engine %d", mode);
     PPO_CUDA(cudaSetDevice(ctx->device));
     Scope sc;
     float *dXp, *dWp, *dB, *dDY = nullptr, *dOut, *dOut2;
@@ -291,6 +348,55 @@ extern "C" int ppo_dense_op(ppo_ctx* ctx, int mode, int op, int64_t M, int K, in
         if (op == 0) PPO_TRY(launch_linear_fwd_simt(ctx, dXp, dWp, dB, dOut, M, K, N, act, slope));
         else if (op == 1) PPO_TRY(launch_linear_dgrad_simt(ctx, dDY, dWp, dXp, dOut, M, K, N, slope));
         else PPO_TRY(launch_linear_wgrad_simt(ctx, dXp, dDY, dOut, dOut2, M, K, N, part, pb));
+    } else if (mode == PPO_GEMM_F16X3_TC) {
+        // fp16-split engine: operands as scaled fp16 hi/lo pairs; output scale from the same guaranteed bound the
+        // policy path uses (max|X| * max column abs-sum of W + max|b|, resp. max|dY| * max row abs-sum), host-evaluated
+        __half *Xh, *Xl, *Wh, *Wl, *WTh, *WTl, *DYh = nullptr, *DYl = nullptr, *Oh, *Ol;
+        float *scs, *part; unsigned* st;
+        PPO_TRY(sc.alloc(&Xh, (size_t)M * K + 128)); PPO_TRY(sc.alloc(&Xl, (size_t)M * K + 128));
+        PPO_TRY(sc.alloc(&Wh, (size_t)K * N)); PPO_TRY(sc.alloc(&Wl, (size_t)K * N));
+        PPO_TRY(sc.alloc(&WTh, (size_t)K * N)); PPO_TRY(sc.alloc(&WTl, (size_t)K * N));
+        PPO_TRY(sc.alloc(&Oh, out_elems + 128)); PPO_TRY(sc.alloc(&Ol, out_elems + 128));
+        PPO_TRY(sc.alloc(&scs, 16)); PPO_TRY(sc.alloc(&st, 4));
+        PPO_CUDA(cudaMemsetAsync(st, 0, 16, s));
+        float *sX = scs, *sW = scs + 2, *sDY = scs + 4, *sO = scs + 6;
+        PPO_TRY(f16_test_operand(ctx, dXp, Xh, Xl, M * K, sX, st));
+        PPO_TRY(f16_test_weight(ctx, dWp, Wh, Wl, WTh, WTl, K, N, sW, st));
+        if (dDY) {
+            PPO_TRY(sc.alloc(&DYh, (size_t)M * N + 128)); PPO_TRY(sc.alloc(&DYl, (size_t)M * N + 128));
+            PPO_TRY(f16_test_operand(ctx, dDY, DYh, DYl, M * N, sDY, st));
+        }
+        double xmax = 0.0, dymax = 0.0, bmax = 0.0, colmax = 0.0, rowmax = 0.0;
+        for (int64_t i = 0; i < M * K; ++i) xmax = std::max(xmax, (double)fabsf(X[i]));
+        if (dY) for (int64_t i = 0; i < M * N; ++i) dymax = std::max(dymax, (double)fabsf(dY[i]));
+        if (bias) for (int n = 0; n < N; ++n) bmax = std::max(bmax, (double)fabsf(bias[n]));
+        {
+            std::vector<double> col(N, 0.0);
+            for (int k = 0; k < K; ++k) {
+                double r = 0.0;
+                for (int n = 0; n < N; ++n) { const double a = fabsf(W[(size_t)k * N + n]); r += a; col[n] += a; }
+                rowmax = std::max(rowmax, r);
+            }
+            for (int n = 0; n < N; ++n) colmax = std::max(colmax, col[n]);
+        }
+        if (op == 0) {
+            PPO_TRY(f16_test_set_scale(ctx, sO, (float)((xmax * colmax + bmax) * 1.001)));
+            PPO_TRY(f16_test_fwd(ctx, Xh, Xl, WTh, WTl, dB, Oh, Ol, M, K, N, act ? 1 : 0, slope, sX, sW, sO));
+            PPO_TRY(f16_test_join(ctx, Oh, Ol, (int64_t)out_elems, sO, dOut));
+        } else if (op == 1) {
+            float *cs_scratch, *cs_out;
+            PPO_TRY(sc.alloc((char**)&cs_scratch, f16_test_partial_bytes(ctx, M, K, N)));
+            PPO_TRY(sc.alloc(&cs_out, (size_t)K));
+            PPO_TRY(f16_test_set_scale(ctx, sO, (float)(dymax * rowmax * 1.001)));
+            PPO_TRY(f16_test_dgrad(ctx, DYh, DYl, Wh, Wl, Xh, Oh, Ol, M, K, N, slope, cs_scratch, cs_out, sDY, sW, sO));
+            PPO_TRY(f16_test_join(ctx, Oh, Ol, (int64_t)out_elems, sO, dOut));
+            if (out2) PPO_CUDA(cudaMemcpyAsync(out2, cs_out, (size_t)K * 4, cudaMemcpyDeviceToHost, s));
+        } else {
+            const size_t pb = f16_test_partial_bytes(ctx, M, K, N);
+            PPO_TRY(sc.alloc((char**)&part, pb));
+            PPO_TRY(f16_test_wgrad(ctx, Xh, Xl, DYh, DYl, dOut, part, pb, M, K, N, sX, sDY));
+            PPO_CUDA(cudaMemsetAsync(dOut2, 0, (size_t)N * 4, s));     // the bias gradient comes from the kernel that produced dY
+        }
     } else {
         // tensor-core engine: operands as tf32 hi/lo pairs; the result is hi + lo of the output pair
         float *Xh, *Xl, *Wh, *Wl, *WTh, *WTl, *DYh = nullptr, *DYl = nullptr, *Ol, *part;

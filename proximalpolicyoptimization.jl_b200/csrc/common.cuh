@@ -122,6 +122,7 @@ struct ppo_policy {
     int64_t hist_cap = 0;
     // tensor-core operand copies (tcgen05 modes), maintained by the Adam kernel / policy_write
     void* tc = nullptr;
+    void* f16 = nullptr;              // fp16-split engine state (gemm_f16.cu)
     // own minibatch staging for the host-array entry points
     ppo_batch hbatch;
 };

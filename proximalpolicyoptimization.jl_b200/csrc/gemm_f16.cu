@@ -1,0 +1,1356 @@
+// gemm_f16.cu — K5/K7 engine PPO_GEMM_F16X3_TC: fp32-grade GEMMs on tcgen05.mma.kind::f16.
+//
+// The reference's policy MLP (test/policy.jl:9-31) is Float32 end to end and parity is stated at 1e-5.
+// kind::f16 runs at twice the kind::tf32 rate and its operands take half the bytes, so this engine keeps
+// every GEMM operand as an fp16 PAIR of a power-of-two-scaled tensor:
+//        T~ = T * 2^e,     hi = fp16_rn(T~),     lo = fp16_rn(T~ - hi)           (22 significant bits)
+//        A B ~= (A_hi B_hi + A_hi B_lo + A_lo B_hi) * 2^-(eA + eB)              (error ~2^-22 per product)
+// i.e. the same error-compensated 3-pass scheme as the tf32 engine (gemm_tc.cu) at twice the tensor rate
+// and HALF the HBM/L2 bytes (a pair costs 4 B/element, like the plain fp32 tensor).
+//
+// fp16 has a 5-bit exponent, so each tensor carries its own exponent e, chosen ON THE DEVICE from a
+// guaranteed upper bound B >= max|T| such that B * 2^e <= 2^14 (no overflow, ever):
+//   * inputs / weights / dlogits: exact abs-max (absmax_kernel, wstats_kernel);
+//   * forward activations:  B(act[l+1]) = B(act[l]) * max_n sum_k |W[k][n]| + max|b|     (plan_fwd_kernel)
+//   * backward activations: B(dZ[l-1])  = B(dZ[l])  * max_k sum_n |W[k][n]|              (plan_bwd_kernel)
+// The bounds are loose by ~2^4 per layer, which costs nothing: fp16 subnormals keep the absolute error of a
+// scaled element <= 2^-25, i.e. <= 2^-25 / 2^14-looseness of the tensor's max (tests hold 1e-5 = 2^-16.6).
+// Scales are exact powers of two, so scaling/unscaling introduces no rounding.
+//
+// Kernels (all sm_100a, hand-written):
+//   f16_gemm_kk_kernel  forward / dgrad: persistent, warp-specialised (TMA warp, one MMA thread, 8 epilogue
+//                       warps), UMMA 128 x BN x 16, 64-element k-blocks (128-byte swizzle rows), contraction
+//                       cut into 128-element chains folded into fp32 registers with round-to-nearest adds
+//                       (the tensor core accumulates with round-toward-zero), epilogue = unscale + bias +
+//                       leakyrelu (or leakyrelu' gate + bias-gradient column sums), rescale, fp16 split,
+//                       swizzled staging, TMA store.
+//   f16_gemm_mn_kernel  wgrad: both operands MN-major straight from the row-major activations (3-D tensor
+//                       maps produce the canonical MN-major SWIZZLE_128B atoms), split over rows, fixed-order
+//                       reduction (deterministic).
+//   head_fwd16 / head_bwd16  the Dense(H, apa) head (N = apa <= 4 is too narrow for a UMMA tile): streaming
+//                       kernels over the fp16 pairs.
+#include <cuda.h>
+#include <cuda_fp16.h>
+
+#include <algorithm>
+
+#include "gemm_f16.cuh"
+#include "tc_ptx.cuh"
+
+namespace ppo {
+
+namespace {
+
+constexpr int F_BM = 128;
+constexpr int F_BK = 64;                    // 64 fp16 = one 128-byte swizzle row
+constexpr int F_STAGES = 2;
+constexpr int F_CHUNK_KB = 2;               // k-blocks per TMEM accumulation chain (128 elements = 24 MMAs)
+constexpr int F_EPI_THREADS = 256;          // 8 epilogue warps: 4 lane quarters x 2 column halves
+constexpr int F_THREADS = 64 + F_EPI_THREADS;
+constexpr int FA_TILE_BYTES = F_BM * F_BK * 2;   // 16 KB
+constexpr int F_MAX_LAYERS = 8;
+constexpr int F_EXP_TARGET = 14;            // bound * 2^e <= 2^14 (fp16 max is ~2^16)
+constexpr int F_EXP_CLAMP = 60;
+
+enum { F_EPI_FWD = 0, F_EPI_DGRAD = 1 };
+
+__device__ __forceinline__ uint32_t pack_h2(__half a, __half b) {
+    return (uint32_t)__half_as_ushort(a) | ((uint32_t)__half_as_ushort(b) << 16);
+}
+// hi = fp16_rn(a), lo = fp16_rn(a - hi); a is already scaled into fp16 range
+__device__ __forceinline__ void f16_split(float a, __half& hi, __half& lo) {
+    hi = __float2half_rn(a);
+    lo = __float2half_rn(a - __half2float(hi));
+}
+// the same, but a strictly positive value never loses its sign to underflow (the backward pass gates on sign(hi))
+__device__ __forceinline__ void f16_split_keep_sign(float a, __half& hi, __half& lo) {
+    hi = __float2half_rn(a);
+    if (a > 0.0f && __half_as_ushort(hi) == 0) hi = __ushort_as_half((unsigned short)1);
+    lo = __float2half_rn(a - __half2float(hi));
+}
+__device__ __forceinline__ void unpack8(const uint4& q, float* x) {
+    const __half2* h = reinterpret_cast<const __half2*>(&q);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float2 f = __half22float2(h[i]);
+        x[2 * i] = f.x; x[2 * i + 1] = f.y;
+    }
+}
+
+struct KK16Params {
+    int M, N, K;
+    int tiles_m, tiles_n, k_blocks;
+    int epi;
+    int act;                 // fwd: apply leakyrelu
+    float slope;
+    const float* bias;       // fwd
+    const __half* gate;      // dgrad: hi half of the activation whose sign gates the gradient, [M][N]
+    float* colsum_partial;   // dgrad: [tiles_m][4][N] column sums of the (unscaled) output per 32-row quarter
+    const float* sc_a;       // {scale, 1/scale} of the A operand
+    const float* sc_b;
+    const float* sc_c;       // of the output
+};
+
+template <int BN>
+struct KK16Smem {
+    static constexpr int B_TILE_BYTES = BN * F_BK * 2;
+    static constexpr int STAGE_BYTES = 2 * FA_TILE_BYTES + 2 * B_TILE_BYTES;
+    // 4 independent store groups (row half x column half, 2 warps each); each stages 64 rows x 32 columns
+    // of hi and of lo (2 x 4 KB) for its own TMA stores
+    static constexpr int STAGING_BYTES = 4 * 2 * 64 * 32 * 2;
+    static constexpr int TOTAL = F_STAGES * STAGE_BYTES + STAGING_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+template <int CPT>
+__device__ __forceinline__ void drain_chunk16(uint32_t taddr, float* s) {
+#pragma unroll
+    for (int c4 = 0; c4 < CPT / 32; ++c4) {
+        float v[32];
+        tmem_ld32(taddr + (uint32_t)(c4 * 32), v);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) s[c4 * 32 + j] += v[j];
+    }
+}
+
+// column sums of a warp's 32 rows x 16 columns (one column set per thread register) with a halving
+// butterfly (16 shuffles); lanes with (lane & 1) == 0 end up holding the sum of column cidx
+__device__ __forceinline__ void colsum16(const float* v, int lane, float& out, int& cidx) {
+    float k8[8], k4[4], k2[2], k1;
+    const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4, b1 = lane & 2;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const float send = b4 ? v[i] : v[i + 8];
+        k8[i] = (b4 ? v[i + 8] : v[i]) + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float send = b3 ? k8[i] : k8[i + 4];
+        k4[i] = (b3 ? k8[i + 4] : k8[i]) + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const float send = b2 ? k4[i] : k4[i + 2];
+        k2[i] = (b2 ? k4[i + 2] : k4[i]) + __shfl_xor_sync(0xffffffffu, send, 4);
+    }
+    {
+        const float send = b1 ? k2[0] : k2[1];
+        k1 = (b1 ? k2[1] : k2[0]) + __shfl_xor_sync(0xffffffffu, send, 2);
+    }
+    k1 += __shfl_xor_sync(0xffffffffu, k1, 1);
+    out = k1;
+    cidx = (b4 ? 8 : 0) + (b3 ? 4 : 0) + (b2 ? 2 : 0) + (b1 ? 1 : 0);
+}
+
+template <int BN>
+__global__ void __launch_bounds__(F_THREADS, 1)
+f16_gemm_kk_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+                   const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
+                   const __grid_constant__ CUtensorMap tmC_hi, const __grid_constant__ CUtensorMap tmC_lo,
+                   const KK16Params p) {
+    using S = KK16Smem<BN>;
+    constexpr int CPT = BN / 2;   // columns per epilogue thread
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    unsigned char* staging = smem + F_STAGES * S::STAGE_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(staging + S::STAGING_BYTES);
+    uint64_t* full = bars;                    // [F_STAGES]
+    uint64_t* empty = bars + F_STAGES;        // [F_STAGES]
+    uint64_t* tfull = bars + 2 * F_STAGES;    // [2]
+    uint64_t* tempty = tfull + 2;             // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int num_tiles = p.tiles_m * p.tiles_n;
+    const int chunks_per_tile = (p.k_blocks + F_CHUNK_KB - 1) / F_CHUNK_KB;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < F_STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(tfull + a, 1); mbar_init(tempty + a, F_EPI_THREADS); }
+        fence_barrier_init();
+        tma_prefetch_desc(&tmA_hi); tma_prefetch_desc(&tmA_lo); tma_prefetch_desc(&tmB_hi); tma_prefetch_desc(&tmB_lo);
+        tma_prefetch_desc(&tmC_hi); tma_prefetch_desc(&tmC_lo);
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, 2 * BN);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int m0 = (tile / p.tiles_n) * F_BM, n0 = (tile % p.tiles_n) * BN;
+                for (int kb = 0; kb < p.k_blocks; ++kb) {
+                    mbar_wait(empty + stage, phase ^ 1);
+                    unsigned char* st = smem + stage * S::STAGE_BYTES;
+                    mbar_expect_tx(full + stage, (uint32_t)S::STAGE_BYTES);
+                    const int k0 = kb * F_BK;
+                    tma_load_2d(st, &tmA_hi, k0, m0, full + stage);
+                    tma_load_2d(st + FA_TILE_BYTES, &tmA_lo, k0, m0, full + stage);
+                    tma_load_2d(st + 2 * FA_TILE_BYTES, &tmB_hi, k0, n0, full + stage);
+                    tma_load_2d(st + 2 * FA_TILE_BYTES + S::B_TILE_BYTES, &tmB_lo, k0, n0, full + stage);
+                    if (++stage == F_STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (one thread) =====================
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_f16(F_BM, BN, 0, 0);
+            int stage = 0; uint32_t phase = 0;
+            uint32_t cc = 0;   // accumulation chains issued so far
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                for (int kb = 0; kb < p.k_blocks; ++cc) {
+                    const int acc = (int)(cc & 1u);
+                    mbar_wait(tempty + acc, ((cc >> 1) & 1u) ^ 1u);
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+                    const int kb_end = kb + F_CHUNK_KB < p.k_blocks ? kb + F_CHUNK_KB : p.k_blocks;
+                    for (int kc = 0; kb < kb_end; ++kb, ++kc) {
+                        mbar_wait(full + stage, phase);
+                        tc_fence_after();
+                        const uint32_t sa = smem_u32(smem + stage * S::STAGE_BYTES);
+                        const uint64_t a_hi = make_desc(sa, 16, 1024);
+                        const uint64_t a_lo = make_desc(sa + FA_TILE_BYTES, 16, 1024);
+                        const uint64_t b_hi = make_desc(sa + 2 * FA_TILE_BYTES, 16, 1024);
+                        const uint64_t b_lo = make_desc(sa + 2 * FA_TILE_BYTES + S::B_TILE_BYTES, 16, 1024);
+#pragma unroll
+                        for (int k = 0; k < F_BK / 16; ++k) {
+                            const uint64_t koff = (uint64_t)(k * 2);   // 16 fp16 = 32 bytes = 2 x 16 B
+                            umma_f16(d_tmem, a_lo + koff, b_hi + koff, idesc, (kc | k) != 0 ? 1u : 0u);
+                            umma_f16(d_tmem, a_hi + koff, b_lo + koff, idesc, 1u);
+                            umma_f16(d_tmem, a_hi + koff, b_hi + koff, idesc, 1u);
+                        }
+                        tc_commit(empty + stage);            // frees the smem slot when these MMAs retire
+                        if (kb == kb_end - 1) tc_commit(tfull + acc);
+                        if (++stage == F_STAGES) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else {
+        // ===================== epilogue: 8 warps = 4 lane quarters x 2 column halves =====================
+        const int q = warp & 3;                        // TMEM lane quarter this warp may access
+        const int half = (warp - 2) >> 2;              // which BN/2 columns
+        const int row_in_tile = q * 32 + lane;
+        // store group = (row half, column half): two warps, 64 rows x CPT columns, own staging + own TMA stores
+        const int rh = q >> 1;
+        const int grp = rh * 2 + half;
+        const int rg = (q & 1) * 32 + lane;            // row within the group's 64 rows
+        uint4* st_hi = reinterpret_cast<uint4*>(staging + grp * 8192);
+        uint4* st_lo = st_hi + 64 * 4;                 // + 4096 B
+        const bool storer = ((q & 1) == 0) && lane == 0;
+        const float unscale = __ldg(p.sc_a + 1) * __ldg(p.sc_b + 1);
+        const float cscale = __ldg(p.sc_c);
+        uint32_t cc = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            const int m0 = (tile / p.tiles_n) * F_BM, n0 = (tile % p.tiles_n) * BN;
+            const int row = m0 + row_in_tile;
+            float s[CPT];
+#pragma unroll
+            for (int j = 0; j < CPT; ++j) s[j] = 0.0f;
+            if (p.epi == F_EPI_DGRAD && row < p.M) {
+                // the gate values are needed only after the whole contraction: pull their lines towards the SM now
+                const char* gp = reinterpret_cast<const char*>(p.gate + (size_t)row * p.N + n0 + half * CPT);
+#pragma unroll
+                for (int l = 0; l < CPT * 2 / 128; ++l)
+                    if (n0 + half * CPT + l * 64 < p.N) asm volatile("prefetch.global.L2 [%0];" ::"l"(gp + l * 128));
+            }
+            for (int ch = 0; ch < chunks_per_tile; ++ch, ++cc) {
+                const int acc = (int)(cc & 1u);
+                mbar_wait(tfull + acc, (cc >> 1) & 1u);
+                tc_fence_after();
+                drain_chunk16<CPT>(tmem_base + (uint32_t)(acc * BN + half * CPT) + ((uint32_t)(q * 32) << 16), s);
+                tc_fence_before();
+                mbar_arrive(tempty + acc);
+            }
+            // ---- unscale, bias / activation (or gradient gate), rescale, fp16 split, staged TMA store (32 columns at a time)
+#pragma unroll
+            for (int g = 0; g < CPT / 32; ++g) {
+                const int col0 = n0 + half * CPT + g * 32;
+                float* v = s + g * 32;
+                if (p.epi == F_EPI_FWD) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const int col = col0 + j;
+                        const float x = fmaf(v[j], unscale, (p.bias != nullptr && col < p.N) ? __ldg(p.bias + col) : 0.0f);
+                        v[j] = (p.act && !(x > 0.0f)) ? p.slope * x : x;
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] *= unscale;
+                    if (row < p.M && col0 + 32 <= p.N) {
+                        const uint4* gp = reinterpret_cast<const uint4*>(p.gate + (size_t)row * p.N + col0);
+#pragma unroll
+                        for (int j8 = 0; j8 < 4; ++j8) {
+                            const uint4 hq = __ldg(gp + j8);
+                            float h[8];
+                            unpack8(hq, h);
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) v[8 * j8 + j] = (h[j] > 0.0f) ? v[8 * j8 + j] : p.slope * v[8 * j8 + j];
+                        }
+                    } else if (row < p.M) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (col0 + j < p.N) {
+                                const float h = __half2float(p.gate[(size_t)row * p.N + col0 + j]);
+                                v[j] = (h > 0.0f) ? v[j] : p.slope * v[j];
+                            }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = 0.0f;     // rows beyond M: keep them out of the column sums
+                    }
+                }
+                if (p.colsum_partial != nullptr) {
+                    // = the bias gradient of the layer below, fused here so that dX is never re-read for it
+#pragma unroll
+                    for (int hh = 0; hh < 2; ++hh) {
+                        float cs; int cidx;
+                        colsum16(v + 16 * hh, lane, cs, cidx);
+                        if ((lane & 1) == 0 && col0 + 16 * hh + cidx < p.N)
+                            p.colsum_partial[((size_t)(tile / p.tiles_n) * 4 + q) * p.N + col0 + 16 * hh + cidx] = cs;
+                    }
+                }
+                if (storer) bulk_wait_read0();        // the group's previous TMA stores have read its staging tile
+                named_bar_sync(1 + grp, 64);
+                // 64-byte rows, SWIZZLE_64B: 16-byte chunk j8 of row r goes to chunk j8 ^ ((r >> 1) & 3)
+#pragma unroll
+                for (int j8 = 0; j8 < 4; ++j8) {
+                    __half h[8], l[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        if (p.epi == F_EPI_FWD) f16_split_keep_sign(v[8 * j8 + j] * cscale, h[j], l[j]);
+                        else f16_split(v[8 * j8 + j] * cscale, h[j], l[j]);
+                    }
+                    const int sw = j8 ^ ((rg >> 1) & 3);
+                    st_hi[rg * 4 + sw] = make_uint4(pack_h2(h[0], h[1]), pack_h2(h[2], h[3]), pack_h2(h[4], h[5]), pack_h2(h[6], h[7]));
+                    st_lo[rg * 4 + sw] = make_uint4(pack_h2(l[0], l[1]), pack_h2(l[2], l[3]), pack_h2(l[4], l[5]), pack_h2(l[6], l[7]));
+                }
+                fence_proxy_async_smem();
+                named_bar_sync(1 + grp, 64);
+                if (storer) {
+                    tma_store_2d(&tmC_hi, st_hi, col0, m0 + rh * 64);
+                    tma_store_2d(&tmC_lo, st_lo, col0, m0 + rh * 64);
+                    bulk_commit();
+                }
+            }
+        }
+        if (storer) bulk_wait_all0();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, 2 * BN);
+}
+
+// ---------------------------------------------------------------------------------------------
+// mn kernel: wgrad.  D[Kin(128-tile), Nout(BN-tile)] = sum over the CTA's row range of X[m,:]^T dY[m,:]
+// (both scaled; the reduction kernel multiplies by 2^-(eX + edY))
+// ---------------------------------------------------------------------------------------------
+struct MN16Params {
+    int Kin, Nout;
+    int64_t M;
+    int tiles_k, tiles_n, splits;
+    int64_t rows_per_split;   // multiple of F_CHUNK_KB * F_BK
+    float* partial;           // [splits][Kin][Nout]
+};
+
+template <int BN>
+__global__ void __launch_bounds__(F_THREADS, 1)
+f16_gemm_mn_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+                   const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
+                   const MN16Params p) {
+    constexpr int B_TILE_BYTES = BN * F_BK * 2;
+    constexpr int STAGE_BYTES = 2 * FA_TILE_BYTES + 2 * B_TILE_BYTES;
+    constexpr int CPT = BN / 2;
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + F_STAGES * STAGE_BYTES);
+    uint64_t* full = bars;
+    uint64_t* empty = bars + F_STAGES;
+    uint64_t* tfull = bars + 2 * F_STAGES;   // [2]
+    uint64_t* tempty = tfull + 2;            // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tile = blockIdx.x % (p.tiles_k * p.tiles_n);
+    const int split = blockIdx.x / (p.tiles_k * p.tiles_n);
+    const int kin0 = (tile / p.tiles_n) * F_BM, n0 = (tile % p.tiles_n) * BN;
+    const int64_t r_begin = (int64_t)split * p.rows_per_split;
+    int64_t r_end = r_begin + p.rows_per_split;
+    if (r_end > p.M) r_end = p.M;
+    const int k_blocks = r_end > r_begin ? (int)((r_end - r_begin + F_BK - 1) / F_BK) : 0;
+    const int chunks = (k_blocks + F_CHUNK_KB - 1) / F_CHUNK_KB;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < F_STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(tfull + a, 1); mbar_init(tempty + a, F_EPI_THREADS); }
+        fence_barrier_init();
+        tma_prefetch_desc(&tmA_hi); tma_prefetch_desc(&tmA_lo); tma_prefetch_desc(&tmB_hi); tma_prefetch_desc(&tmB_lo);
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, 2 * BN);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int kb = 0; kb < k_blocks; ++kb) {
+                mbar_wait(empty + stage, phase ^ 1);
+                unsigned char* st = smem + stage * STAGE_BYTES;
+                mbar_expect_tx(full + stage, (uint32_t)STAGE_BYTES);
+                const int r0 = (int)(r_begin + (int64_t)kb * F_BK);
+                // box {64 cols, 64 rows, 2 (or BN/64) column blocks}: rows beyond M are zero-filled
+                tma_load_3d(st, &tmA_hi, 0, r0, kin0 / 64, full + stage);
+                tma_load_3d(st + FA_TILE_BYTES, &tmA_lo, 0, r0, kin0 / 64, full + stage);
+                tma_load_3d(st + 2 * FA_TILE_BYTES, &tmB_hi, 0, r0, n0 / 64, full + stage);
+                tma_load_3d(st + 2 * FA_TILE_BYTES + B_TILE_BYTES, &tmB_lo, 0, r0, n0 / 64, full + stage);
+                if (++stage == F_STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_f16(F_BM, BN, 1, 1);
+            int stage = 0; uint32_t phase = 0;
+            int kb = 0;
+            for (uint32_t cc = 0; kb < k_blocks; ++cc) {
+                const int acc = (int)(cc & 1u);
+                mbar_wait(tempty + acc, ((cc >> 1) & 1u) ^ 1u);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+                const int kb_end = (kb + F_CHUNK_KB < k_blocks) ? kb + F_CHUNK_KB : k_blocks;
+                for (int kc = 0; kb < kb_end; ++kb, ++kc) {
+                    mbar_wait(full + stage, phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+                    // MN-major fp16, SWIZZLE_128B: an atom is 8 k-rows x 128 B (64 columns).  The 64-column blocks
+                    // are F_BK rows * 128 B = 8192 B apart (LBO); consecutive 8-row atoms along k are 1024 B apart
+                    // (SBO); one MMA (K = 16) consumes two of them = 2048 B per k-step.
+                    const uint64_t a_hi = make_desc(sa, 8192, 1024);
+                    const uint64_t a_lo = make_desc(sa + FA_TILE_BYTES, 8192, 1024);
+                    const uint64_t b_hi = make_desc(sa + 2 * FA_TILE_BYTES, 8192, 1024);
+                    const uint64_t b_lo = make_desc(sa + 2 * FA_TILE_BYTES + B_TILE_BYTES, 8192, 1024);
+#pragma unroll
+                    for (int k = 0; k < F_BK / 16; ++k) {
+                        const uint64_t koff = (uint64_t)(k * 128);   // 2048 B per k-step
+                        umma_f16(d_tmem, a_lo + koff, b_hi + koff, idesc, (kc | k) != 0 ? 1u : 0u);
+                        umma_f16(d_tmem, a_hi + koff, b_lo + koff, idesc, 1u);
+                        umma_f16(d_tmem, a_hi + koff, b_hi + koff, idesc, 1u);
+                    }
+                    tc_commit(empty + stage);
+                    if (kb == kb_end - 1) tc_commit(tfull + acc);
+                    if (++stage == F_STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else {
+        const int q = warp & 3;
+        const int half = (warp - 2) >> 2;
+        const int row = kin0 + q * 32 + lane;
+        float s[CPT];
+#pragma unroll
+        for (int j = 0; j < CPT; ++j) s[j] = 0.0f;
+        for (uint32_t cc = 0; cc < (uint32_t)chunks; ++cc) {
+            const int acc = (int)(cc & 1u);
+            mbar_wait(tfull + acc, (cc >> 1) & 1u);
+            tc_fence_after();
+            drain_chunk16<CPT>(tmem_base + (uint32_t)(acc * BN + half * CPT) + ((uint32_t)(q * 32) << 16), s);
+            tc_fence_before();
+            mbar_arrive(tempty + acc);
+        }
+        if (row < p.Kin) {
+            float* out = p.partial + ((size_t)split * p.Kin + (size_t)row) * p.Nout;
+            const int col0 = n0 + half * CPT;
+            if (col0 + CPT <= p.Nout && (p.Nout & 3) == 0) {
+#pragma unroll
+                for (int j4 = 0; j4 < CPT / 4; ++j4)
+                    reinterpret_cast<float4*>(out + col0)[j4] = make_float4(s[4 * j4], s[4 * j4 + 1], s[4 * j4 + 2], s[4 * j4 + 3]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < CPT; ++j)
+                    if (col0 + j < p.Nout) out[col0 + j] = s[j];
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, 2 * BN);
+}
+
+// ---------------------------------------------------------------------------------------------
+// scales: statistics, planning, splitting
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float block_max_256(float m) {
+    __shared__ float sm[8];
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, d));
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = m;
+    __syncthreads();
+    float r = sm[0];
+#pragma unroll
+    for (int i = 1; i < 8; ++i) r = fmaxf(r, sm[i]);
+    __syncthreads();
+    return r;
+}
+
+// out = max(out, max |x|) as the bit pattern of a non-negative float (order-preserving, deterministic)
+__global__ void __launch_bounds__(256)
+absmax_kernel(const float* __restrict__ x, int64_t n, unsigned* out) {
+    float m = 0.0f;
+    const int64_t n4 = n >> 2;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(x) + i);
+        m = fmaxf(fmaxf(m, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (n & 3)) m = fmaxf(m, fabsf(x[(n4 << 2) + threadIdx.x]));
+    m = block_max_256(m);
+    if (threadIdx.x == 0 && m > 0.0f) atomicMax(out, __float_as_uint(m));
+}
+
+__device__ __forceinline__ void write_scale(float* sc, float bound) {
+    int e = 0;
+    if (bound > 0.0f && bound < INFINITY) {
+        int ex;
+        frexpf(bound, &ex);                       // bound = m * 2^ex, m in [0.5, 1)  =>  bound <= 2^ex
+        e = F_EXP_TARGET - ex;
+        e = e < -F_EXP_CLAMP ? -F_EXP_CLAMP : (e > F_EXP_CLAMP ? F_EXP_CLAMP : e);
+    }
+    sc[0] = ldexpf(1.0f, e);
+    sc[1] = ldexpf(1.0f, -e);
+}
+
+struct F16LayerTable {
+    int L;                          // Dense layers (hidden + head)
+    int K[F_MAX_LAYERS], N[F_MAX_LAYERS];
+    long long w_off[F_MAX_LAYERS], b_off[F_MAX_LAYERS];
+};
+
+// stats[l][0..3] = {max |W|, max_n sum_k |W[k][n]|, max_k sum_n |W[k][n]|, max |b|}; grid (blocks, L)
+__global__ void __launch_bounds__(256)
+wstats_kernel(const float* __restrict__ params, F16LayerTable t, unsigned* stats) {
+    const int l = blockIdx.y;
+    const int K = t.K[l], N = t.N[l];
+    const int nbc = (N + 255) / 256, nbr = (K + 255) / 256;
+    if ((int)blockIdx.x >= nbc + nbr) return;
+    const float* W = params + t.w_off[l];
+    const float* b = params + t.b_off[l];
+    float amax = 0.0f, colmax = 0.0f, rowmax = 0.0f, bmax = 0.0f;
+    if ((int)blockIdx.x < nbc) {
+        const int n = blockIdx.x * 256 + threadIdx.x;
+        if (n < N) {
+            float s = 0.0f;
+            for (int k = 0; k < K; ++k) { const float a = fabsf(W[(size_t)k * N + n]); s += a; amax = fmaxf(amax, a); }
+            colmax = s;
+            bmax = fabsf(b[n]);
+        }
+    } else {
+        const int k = (blockIdx.x - nbc) * 256 + threadIdx.x;
+        if (k < K) {
+            float s = 0.0f;
+            for (int n = 0; n < N; ++n) s += fabsf(W[(size_t)k * N + n]);
+            rowmax = s;
+        }
+    }
+    amax = block_max_256(amax); colmax = block_max_256(colmax); rowmax = block_max_256(rowmax); bmax = block_max_256(bmax);
+    if (threadIdx.x == 0) {
+        unsigned* st = stats + 4 * l;
+        if (amax > 0.0f) atomicMax(st + 0, __float_as_uint(amax));
+        if (colmax > 0.0f) atomicMax(st + 1, __float_as_uint(colmax));
+        if (rowmax > 0.0f) atomicMax(st + 2, __float_as_uint(rowmax));
+        if (bmax > 0.0f) atomicMax(st + 3, __float_as_uint(bmax));
+    }
+}
+
+// scale slots (pairs {scale, 1/scale}): 0 = X0, l = act[l] (l = 1..L-1), L + l = W_l (l = 0..L-2),
+// 2L - 1 + l = dZ_l, the gradient at the output of hidden layer l (l = 0..L-2)
+__host__ __device__ inline int sc_act(int l) { return l; }
+__host__ __device__ inline int sc_w(int L, int l) { return L + l; }
+__host__ __device__ inline int sc_dz(int L, int l) { return 2 * L - 1 + l; }
+
+__global__ void plan_w_kernel(int L, const unsigned* wstats, float* sc) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    for (int l = 0; l + 1 < L; ++l) write_scale(sc + 2 * sc_w(L, l), __uint_as_float(wstats[4 * l]));
+}
+// consumes (and clears) the abs-max of the minibatch features
+__global__ void plan_fwd_kernel(int L, float slope, unsigned* st_x0, const unsigned* wstats, float* sc) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    float B = __uint_as_float(*st_x0);
+    *st_x0 = 0u;
+    write_scale(sc + 2 * sc_act(0), B);
+    const float amp = fmaxf(1.0f, fabsf(slope));
+    for (int l = 0; l + 1 < L; ++l) {
+        B = (B * __uint_as_float(wstats[4 * l + 1]) + __uint_as_float(wstats[4 * l + 3])) * amp;
+        B *= 1.0009765625f;      // the bound itself is evaluated in fp32
+        write_scale(sc + 2 * sc_act(l + 1), B);
+    }
+}
+// consumes (and clears) the abs-max of dlogits
+__global__ void plan_bwd_kernel(int L, float slope, unsigned* st_dl, const unsigned* wstats, float* sc) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    float G = __uint_as_float(*st_dl);
+    *st_dl = 0u;
+    const float amp = fmaxf(1.0f, fabsf(slope));
+    for (int l = L - 1; l >= 1; --l) {      // dZ_{l-1} = (dZ_l W_l^T) .* act'   (dZ_{L-1} = dlogits)
+        G = G * __uint_as_float(wstats[4 * l + 2]) * amp * 1.0009765625f;
+        write_scale(sc + 2 * sc_dz(L, l - 1), G);
+    }
+}
+__global__ void scale_from_stat_kernel(unsigned* st, float* sc) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    write_scale(sc, __uint_as_float(*st));
+    *st = 0u;
+}
+__global__ void scale_from_bound_kernel(float bound, float* sc) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) write_scale(sc, bound);
+}
+
+// x * scale -> (hi, lo), 8 elements per thread
+__global__ void __launch_bounds__(256)
+split16_kernel(const float* __restrict__ x, __half* __restrict__ hi, __half* __restrict__ lo, int64_t n8, const float* sc) {
+    const float s = __ldg(sc);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
+        const float4 a = __ldcs(reinterpret_cast<const float4*>(x) + 2 * i);
+        const float4 b = __ldcs(reinterpret_cast<const float4*>(x) + 2 * i + 1);
+        const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+        __half h[8], l[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f16_split(v[j] * s, h[j], l[j]);
+        reinterpret_cast<uint4*>(hi)[i] = make_uint4(pack_h2(h[0], h[1]), pack_h2(h[2], h[3]), pack_h2(h[4], h[5]), pack_h2(h[6], h[7]));
+        reinterpret_cast<uint4*>(lo)[i] = make_uint4(pack_h2(l[0], l[1]), pack_h2(l[2], l[3]), pack_h2(l[4], l[5]), pack_h2(l[6], l[7]));
+    }
+}
+__global__ void __launch_bounds__(256)
+split16_tail_kernel(const float* x, __half* hi, __half* lo, int64_t begin, int64_t n, const float* sc) {
+    const int64_t i = begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { __half h, l; f16_split(x[i] * __ldg(sc), h, l); hi[i] = h; lo[i] = l; }
+}
+// (hi + lo) / scale -> fp32
+__global__ void __launch_bounds__(256)
+join16_kernel(const __half* __restrict__ hi, const __half* __restrict__ lo, int64_t n, const float* sc, float* __restrict__ out) {
+    const float inv = __ldg(sc + 1);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = (__half2float(hi[i]) + __half2float(lo[i])) * inv;
+}
+
+// W[K][N] * scale -> hi/lo of W and of W^T[N][K]
+__global__ void __launch_bounds__(256)
+weight_prep16_kernel(const float* __restrict__ W, __half* __restrict__ W_hi, __half* __restrict__ W_lo,
+                     __half* __restrict__ WT_hi, __half* __restrict__ WT_lo, int K, int N, const float* sc) {
+    __shared__ float tile[32][33];
+    const float s = __ldg(sc);
+    const int k0 = blockIdx.y * 32, n0 = blockIdx.x * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+    for (int r = ty; r < 32; r += 8) {
+        const int k = k0 + r, n = n0 + tx;
+        const float v = (k < K && n < N) ? W[(size_t)k * N + n] * s : 0.0f;
+        tile[r][tx] = v;
+        if (k < K && n < N) { __half h, l; f16_split(v, h, l); W_hi[(size_t)k * N + n] = h; W_lo[(size_t)k * N + n] = l; }
+    }
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {
+        const int n = n0 + r, k = k0 + tx;
+        if (n < N && k < K) {
+            __half h, l; f16_split(tile[tx][r], h, l);
+            WT_hi[(size_t)n * K + k] = h;
+            WT_lo[(size_t)n * K + k] = l;
+        }
+    }
+}
+
+// out[i] = (sum_z partial[z*stride + i]) * inv(sa) * inv(sb), fixed order
+__global__ void __launch_bounds__(256)
+f16_reduce_kernel(const float* __restrict__ partial, int splits, int64_t stride, int64_t count, float* __restrict__ out,
+                  const float* sa, const float* sb) {
+    const float u = (sa ? __ldg(sa + 1) : 1.0f) * (sb ? __ldg(sb + 1) : 1.0f);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x) {
+        float s = 0.0f;
+        for (int z = 0; z < splits; ++z) s += partial[(size_t)z * stride + i];
+        out[i] = s * u;
+    }
+}
+
+// stage 1 of folding the dgrad epilogue's per-quarter column sums: block (x = column block, y = row chunk)
+__global__ void __launch_bounds__(256)
+f16_colsum_fold_kernel(const float* __restrict__ part, int64_t rows, int N, int64_t rows_per_chunk, float* __restrict__ out) {
+    const int n = blockIdx.x * 256 + threadIdx.x;
+    if (n >= N) return;
+    const int64_t r0 = (int64_t)blockIdx.y * rows_per_chunk;
+    const int64_t r1 = r0 + rows_per_chunk < rows ? r0 + rows_per_chunk : rows;
+    float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
+    int64_t r = r0;
+    for (; r + 3 < r1; r += 4) {
+        s0 += part[r * N + n]; s1 += part[(r + 1) * N + n]; s2 += part[(r + 2) * N + n]; s3 += part[(r + 3) * N + n];
+    }
+    for (; r < r1; ++r) s0 += part[r * N + n];
+    out[(size_t)blockIdx.y * N + n] = (s0 + s1) + (s2 + s3);
+}
+
+// ---------------------------------------------------------------------------------------------
+// the policy head Dense(K, N <= 4) on fp16 pairs
+// ---------------------------------------------------------------------------------------------
+// logits[m][n] = (sum_k (H_hi + H_lo)[m][k] W[k][n]) / scale + b[n]: one warp per token row, two rows in flight.
+// W is staged in shared memory as [c][n][k/8] so that the 32 lanes (consecutive k/8) read consecutive words.
+template <int N>
+__global__ void __launch_bounds__(256)
+head_fwd16_kernel(const __half* __restrict__ H_hi, const __half* __restrict__ H_lo, const float* __restrict__ W,
+                  const float* __restrict__ bias, float* __restrict__ logits, int64_t M, int K, const float* sc_h) {
+    extern __shared__ __align__(16) float sW[];   // [8][N][K/8]
+    const int KV = K >> 3;
+    for (int i = threadIdx.x; i < K * N; i += blockDim.x) {
+        const int k = i / N, n = i % N;
+        sW[((k & 7) * N + n) * KV + (k >> 3)] = W[i];
+    }
+    __syncthreads();
+    const float inv = __ldg(sc_h + 1);
+    const int lane = threadIdx.x & 31;
+    const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int64_t w0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    for (int64_t m = w0; m < M; m += 2 * warps) {
+        const int64_t m2 = m + warps;
+        const bool two = m2 < M;
+        const uint4* hp0 = reinterpret_cast<const uint4*>(H_hi + m * K);
+        const uint4* lp0 = reinterpret_cast<const uint4*>(H_lo + m * K);
+        const uint4* hp1 = reinterpret_cast<const uint4*>(H_hi + (two ? m2 : m) * K);
+        const uint4* lp1 = reinterpret_cast<const uint4*>(H_lo + (two ? m2 : m) * K);
+        float a0[N], a1[N];
+#pragma unroll
+        for (int n = 0; n < N; ++n) { a0[n] = 0.0f; a1[n] = 0.0f; }
+        for (int kv = lane; kv < KV; kv += 32) {
+            const uint4 qh0 = __ldcs(hp0 + kv), ql0 = __ldcs(lp0 + kv), qh1 = __ldcs(hp1 + kv), ql1 = __ldcs(lp1 + kv);
+            float h0[8], l0[8], h1[8], l1[8];
+            unpack8(qh0, h0); unpack8(ql0, l0); unpack8(qh1, h1); unpack8(ql1, l1);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const float v0 = h0[c] + l0[c], v1 = h1[c] + l1[c];
+#pragma unroll
+                for (int n = 0; n < N; ++n) {
+                    const float w = sW[(c * N + n) * KV + kv];
+                    a0[n] = fmaf(v0, w, a0[n]);
+                    a1[n] = fmaf(v1, w, a1[n]);
+                }
+            }
+        }
+#pragma unroll
+        for (int n = 0; n < N; ++n)
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) {
+                a0[n] += __shfl_xor_sync(0xffffffffu, a0[n], d);
+                a1[n] += __shfl_xor_sync(0xffffffffu, a1[n], d);
+            }
+        if (lane == 0) {
+#pragma unroll
+            for (int n = 0; n < N; ++n) {
+                const float bn = bias ? bias[n] : 0.0f;
+                logits[m * N + n] = fmaf(a0[n], inv, bn);
+                if (two) logits[m2 * N + n] = fmaf(a1[n], inv, bn);
+            }
+        }
+    }
+}
+
+// One pass over H (fp16 pair): dH = (dlogits W^T) .* leakyrelu'(H) written as a scaled fp16 pair; per-CTA partials
+// of dW[k][n], db[n] and of the column sums of dH (= the bias gradient of the layer below).
+// Partial layout per CTA: [K*N dW][N db][K colsum(dH)].  Thread t owns the column pairs 2 (t + 256 q), q < KPT.
+template <int N, int KPT>
+__global__ void __launch_bounds__(256)
+head_bwd16_kernel(const __half* __restrict__ H_hi, const __half* __restrict__ H_lo, const float* __restrict__ dlogits,
+                  const float* __restrict__ W, __half* __restrict__ dH_hi, __half* __restrict__ dH_lo,
+                  float* __restrict__ partial, int64_t M, int K, float slope, int64_t rows_per_cta, int need_dH,
+                  const float* sc_h, const float* sc_dh) {
+    const int tid = threadIdx.x;
+    const float inv_h = __ldg(sc_h + 1);
+    const float s_dh = need_dH ? __ldg(sc_dh) : 1.0f;
+    float w[KPT][2][N], aw[KPT][2][N], ab[N], cs[KPT][2];
+#pragma unroll
+    for (int q = 0; q < KPT; ++q)
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            cs[q][c] = 0.0f;
+            const int k = 2 * (tid + q * 256) + c;
+#pragma unroll
+            for (int n = 0; n < N; ++n) {
+                w[q][c][n] = (k < K) ? W[k * N + n] : 0.0f;
+                aw[q][c][n] = 0.0f;
+            }
+        }
+#pragma unroll
+    for (int n = 0; n < N; ++n) ab[n] = 0.0f;
+    const int64_t r0 = (int64_t)blockIdx.x * rows_per_cta;
+    const int64_t r1 = r0 + rows_per_cta < M ? r0 + rows_per_cta : M;
+    constexpr int RU = 4;
+    for (int64_t m = r0; m < r1; m += RU) {
+        __half2 hh[RU][KPT], hl[RU][KPT];
+        float d[RU][N];
+#pragma unroll
+        for (int u = 0; u < RU; ++u) {
+            const bool rv = m + u < r1;
+#pragma unroll
+            for (int q = 0; q < KPT; ++q) {
+                const int k = 2 * (tid + q * 256);
+                uint32_t a = 0u, b = 0u;
+                if (rv && k < K) {
+                    a = __ldcs(reinterpret_cast<const unsigned int*>(H_hi + (m + u) * K + k));
+                    b = __ldcs(reinterpret_cast<const unsigned int*>(H_lo + (m + u) * K + k));
+                }
+                hh[u][q] = *reinterpret_cast<__half2*>(&a);
+                hl[u][q] = *reinterpret_cast<__half2*>(&b);
+            }
+#pragma unroll
+            for (int n = 0; n < N; ++n) d[u][n] = rv ? __ldg(dlogits + (m + u) * N + n) : 0.0f;
+        }
+#pragma unroll
+        for (int u = 0; u < RU; ++u) {
+            const bool rv = m + u < r1;
+#pragma unroll
+            for (int q = 0; q < KPT; ++q) {
+                const int k = 2 * (tid + q * 256);
+                const float2 fh = __half22float2(hh[u][q]), fl = __half22float2(hl[u][q]);
+                const float hv[2] = {fh.x + fl.x, fh.y + fl.y};       // scaled activation
+                const float gate[2] = {fh.x, fh.y};
+                __half oh[2], ol[2];
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    float dx = 0.0f;
+#pragma unroll
+                    for (int n = 0; n < N; ++n) {
+                        dx = fmaf(d[u][n], w[q][c][n], dx);
+                        aw[q][c][n] = fmaf(hv[c], d[u][n], aw[q][c][n]);
+                    }
+                    const float g = (gate[c] > 0.0f) ? dx : slope * dx;
+                    if (rv && k + c < K) cs[q][c] += g;
+                    f16_split(g * s_dh, oh[c], ol[c]);
+                }
+                if (need_dH && rv && k < K) {
+                    *reinterpret_cast<unsigned int*>(dH_hi + (m + u) * K + k) = pack_h2(oh[0], oh[1]);
+                    *reinterpret_cast<unsigned int*>(dH_lo + (m + u) * K + k) = pack_h2(ol[0], ol[1]);
+                }
+            }
+            if (tid == 0) {
+#pragma unroll
+                for (int n = 0; n < N; ++n) ab[n] += d[u][n];
+            }
+        }
+    }
+    float* pw = partial + (int64_t)blockIdx.x * ((int64_t)K * N + N + K);
+#pragma unroll
+    for (int q = 0; q < KPT; ++q)
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            const int k = 2 * (tid + q * 256) + c;
+            if (k < K) {
+#pragma unroll
+                for (int n = 0; n < N; ++n) pw[k * N + n] = aw[q][c][n] * inv_h;
+                pw[(int64_t)K * N + N + k] = cs[q][c];
+            }
+        }
+    if (tid == 0) {
+#pragma unroll
+        for (int n = 0; n < N; ++n) pw[(int64_t)K * N + n] = ab[n];
+    }
+}
+
+inline int64_t head16_ctas(int64_t M, int num_sms) {
+    const int64_t c = (int64_t)num_sms * 4;
+    const int64_t maxc = ceil_div(M, 64);
+    return c < maxc ? c : (maxc < 1 ? 1 : maxc);
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn g_encode16 = nullptr;
+
+int load_encode16() {
+    if (g_encode16) return PPO_OK;
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    PPO_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    if (qres != cudaDriverEntryPointSuccess || fn == nullptr) {
+        set_error("cuTensorMapEncodeTiled not available from the driver");
+        return PPO_ERR_CUDA;
+    }
+    g_encode16 = (EncodeTiledFn)fn;
+    return PPO_OK;
+}
+
+// 2-D map over a row-major [rows][cols] fp16 matrix: box {64 cols, box_rows} with 128B swizzle (operand loads) or
+// {32 cols, box_rows} with 64B swizzle (epilogue stores)
+int make_map16_2d(CUtensorMap* m, const __half* base, int64_t rows, int64_t cols, int box_rows, int box_cols = 64) {
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
+    cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = g_encode16(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void*)base, dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, box_cols == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(f16 2d %lld x %lld) failed: %d", (long long)rows, (long long)cols, (int)r); return PPO_ERR_CUDA; }
+    return PPO_OK;
+}
+// 3-D view of a row-major [rows][cols] fp16 matrix as {64, rows, cols/64}: one box = `blocks` column blocks of
+// F_BK rows each, i.e. the canonical MN-major SWIZZLE_128B operand layout
+int make_map16_mn(CUtensorMap* m, const __half* base, int64_t rows, int64_t cols, int blocks) {
+    cuuint64_t dims[3] = {64, (cuuint64_t)rows, (cuuint64_t)((cols + 63) / 64)};
+    cuuint64_t strides[2] = {(cuuint64_t)cols * 2, 128};
+    cuuint32_t box[3] = {64, (cuuint32_t)F_BK, (cuuint32_t)blocks};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = g_encode16(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, (void*)base, dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(f16 mn %lld x %lld) failed: %d", (long long)rows, (long long)cols, (int)r); return PPO_ERR_CUDA; }
+    return PPO_OK;
+}
+
+struct F16Layer {
+    __half* W_hi = nullptr;   // [K][N]  (dgrad B operand)
+    __half* W_lo = nullptr;
+    __half* WT_hi = nullptr;  // [N][K]  (forward B operand)
+    __half* WT_lo = nullptr;
+};
+
+struct F16State {
+    std::vector<F16Layer> layers;
+    F16LayerTable table{};
+    int64_t tokens = 0;
+    __half* x_hi = nullptr;                  // scaled minibatch features [M][dims[0]] (+ slack)
+    __half* x_lo = nullptr;
+    std::vector<__half*> act_hi, act_lo;     // act[l], l = 1..L-1
+    __half* dz_hi[2] = {nullptr, nullptr};   // ping-pong activation gradients [M][Hmax]
+    __half* dz_lo[2] = {nullptr, nullptr};
+    float* partial = nullptr;
+    size_t partial_bytes = 0;
+    float* sc = nullptr;                     // scale pairs
+    unsigned* st = nullptr;                  // [0] abs-max X0, [1] abs-max dlogits, [2 + 4 l + j] weight statistics
+};
+
+F16State* state(ppo_policy* p) { return reinterpret_cast<F16State*>(p->f16); }
+
+template <typename T>
+void fr(T*& q) { if (q) cudaFree(q); q = nullptr; }
+
+int wgrad_splits16(int64_t M, int tiles, int num_sms) {
+    int s = std::max(1, num_sms / tiles);
+    const int64_t max_s = std::max<int64_t>(1, M / (F_BK * 8));
+    if (s > max_s) s = (int)max_s;
+    return s;
+}
+
+size_t head16_partial_bytes(int64_t M, int K, int N, int num_sms) {
+    return (size_t)head16_ctas(M, num_sms) * ((size_t)K * N + N + K) * sizeof(float);
+}
+
+size_t f16_partial_bytes(int64_t tokens, int K, int N, int num_sms) {
+    const int BN = N > 128 ? 256 : 128;
+    const int tiles = (int)(ceil_div(K, F_BM) * ceil_div(N, BN));
+    const size_t a = (size_t)wgrad_splits16(tokens, tiles, num_sms) * K * N * 4;
+    const size_t c = ((size_t)4 * ceil_div(tokens, F_BM) + 64) * (size_t)std::max(K, N) * 4;   // dgrad-epilogue column sums
+    return std::max(a, c);
+}
+
+int launch_absmax(ppo_ctx* ctx, const float* x, int64_t n, unsigned* out) {
+    const int64_t blocks = std::max<int64_t>(1, std::min<int64_t>(ceil_div(n / 4 + 1, 256), (int64_t)ctx->num_sms * 8));
+    absmax_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(x, n, out);
+    ctx->launches += 1;
+    PPO_CUDA(cudaGetLastError());
+    return PPO_OK;
+}
+
+int launch_split16(ppo_ctx* ctx, const float* x, __half* hi, __half* lo, int64_t n, const float* sc) {
+    const int64_t n8 = n / 8;
+    if (n8 > 0) {
+        const int64_t blocks = std::min<int64_t>(ceil_div(n8, 256), (int64_t)ctx->num_sms * 16);
+        split16_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(x, hi, lo, n8, sc);
+        ctx->launches += 1;
+    }
+    if (n8 * 8 < n) {
+        split16_tail_kernel<<<1, 256, 0, ctx->stream>>>(x, hi, lo, n8 * 8, n, sc);
+        ctx->launches += 1;
+    }
+    PPO_CUDA(cudaGetLastError());
+    return PPO_OK;
+}
+
+template <int BN>
+int launch_kk16(ppo_ctx* ctx, const __half* A, const __half* A_lo, const __half* B, const __half* B_lo, __half* C, __half* C_lo,
+                int64_t M, int N, int K, const KK16Params& base) {
+    CUtensorMap mA, mAl, mB, mBl, mC, mCl;
+    PPO_TRY(make_map16_2d(&mA, A, M, K, F_BM));
+    PPO_TRY(make_map16_2d(&mAl, A_lo, M, K, F_BM));
+    PPO_TRY(make_map16_2d(&mB, B, N, K, BN));
+    PPO_TRY(make_map16_2d(&mBl, B_lo, N, K, BN));
+    PPO_TRY(make_map16_2d(&mC, C, M, N, 64, 32));      // store boxes: 64 rows x 32 columns, SWIZZLE_64B
+    PPO_TRY(make_map16_2d(&mCl, C_lo, M, N, 64, 32));
+    KK16Params p = base;
+    p.M = (int)M; p.N = N; p.K = K;
+    p.tiles_m = (int)ceil_div(M, F_BM); p.tiles_n = (int)ceil_div(N, BN); p.k_blocks = (int)ceil_div(K, F_BK);
+    const int tiles = p.tiles_m * p.tiles_n;
+    const int grid = std::min(tiles, ctx->num_sms);
+    const size_t smem = KK16Smem<BN>::TOTAL;
+    PPO_CUDA(cudaFuncSetAttribute(f16_gemm_kk_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    f16_gemm_kk_kernel<BN><<<grid, F_THREADS, smem, ctx->stream>>>(mA, mAl, mB, mBl, mC, mCl, p);
+    ctx->launches += 1;
+    PPO_CUDA(cudaGetLastError());
+    return PPO_OK;
+}
+
+int kk16_dispatch(ppo_ctx* ctx, const __half* A, const __half* A_lo, const __half* B, const __half* B_lo, __half* C, __half* C_lo,
+                  int64_t M, int N, int K, const KK16Params& base) {
+    PPO_REQUIRE(M < ((int64_t)1 << 31), "f16 gemm: M too large");
+    PPO_REQUIRE(K % 8 == 0 && N % 32 == 0, "f16 gemm: K %% 8 and N %% 32 required (K=%d N=%d)", K, N);
+    if (N > 128) return launch_kk16<256>(ctx, A, A_lo, B, B_lo, C, C_lo, M, N, K, base);
+    return launch_kk16<128>(ctx, A, A_lo, B, B_lo, C, C_lo, M, N, K, base);
+}
+
+template <int BN>
+int launch_mn16(ppo_ctx* ctx, const __half* X, const __half* X_lo, const __half* dY, const __half* dY_lo, int64_t M, int Kin,
+                int Nout, float* partial, int splits) {
+    CUtensorMap mA, mAl, mB, mBl;
+    PPO_TRY(make_map16_mn(&mA, X, M, Kin, F_BM / 64));
+    PPO_TRY(make_map16_mn(&mAl, X_lo, M, Kin, F_BM / 64));
+    PPO_TRY(make_map16_mn(&mB, dY, M, Nout, BN / 64));
+    PPO_TRY(make_map16_mn(&mBl, dY_lo, M, Nout, BN / 64));
+    MN16Params p;
+    p.Kin = Kin; p.Nout = Nout; p.M = M;
+    p.tiles_k = (int)ceil_div(Kin, F_BM); p.tiles_n = (int)ceil_div(Nout, BN); p.splits = splits;
+    p.rows_per_split = round_up(ceil_div(M, splits), F_CHUNK_KB * F_BK);
+    p.partial = partial;
+    const size_t smem = (size_t)F_STAGES * (2 * FA_TILE_BYTES + 2 * BN * F_BK * 2) + 1024 + 256;
+    PPO_CUDA(cudaFuncSetAttribute(f16_gemm_mn_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int grid = p.tiles_k * p.tiles_n * splits;
+    f16_gemm_mn_kernel<BN><<<grid, F_THREADS, smem, ctx->stream>>>(mA, mAl, mB, mBl, p);
+    ctx->launches += 1;
+    PPO_CUDA(cudaGetLastError());
+    return PPO_OK;
+}
+
+// fold [rows][N] per-quarter column sums (rows = 4 * tiles_m) into out[N]; scratch holds 64 * N floats
+int fold_colsum16(ppo_ctx* ctx, const float* part, int64_t rows, int N, float* scratch, float* out) {
+    const int chunks = (int)std::min<int64_t>(64, rows);
+    const int64_t rpc = ceil_div(rows, chunks);
+    dim3 grid((unsigned)ceil_div(N, 256), (unsigned)chunks);
+    f16_colsum_fold_kernel<<<grid, 256, 0, ctx->stream>>>(part, rows, N, rpc, scratch);
+    f16_reduce_kernel<<<(unsigned)ceil_div(N, 256), 256, 0, ctx->stream>>>(scratch, chunks, N, N, out, nullptr, nullptr);
+    ctx->launches += 2;
+    PPO_CUDA(cudaGetLastError());
+    return PPO_OK;
+}
+
+int wgrad16(ppo_ctx* ctx, const __half* X, const __half* X_lo, const __half* dY, const __half* dY_lo, float* dW,
+            float* partial, size_t partial_bytes, int64_t M, int K, int N, const float* sc_x, const float* sc_dy) {
+    PPO_REQUIRE(K % 8 == 0 && N % 32 == 0, "f16 wgrad: K %% 8 and N %% 32 required (K=%d N=%d)", K, N);
+    const int BN = N > 128 ? 256 : 128;
+    const int tiles = (int)(ceil_div(K, F_BM) * ceil_div(N, BN));
+    const int splits = wgrad_splits16(M, tiles, ctx->num_sms);
+    PPO_REQUIRE((size_t)splits * K * N * 4 <= partial_bytes, "f16 wgrad: partial buffer too small");
+    if (BN == 256) PPO_TRY(launch_mn16<256>(ctx, X, X_lo, dY, dY_lo, M, K, N, partial, splits));
+    else PPO_TRY(launch_mn16<128>(ctx, X, X_lo, dY, dY_lo, M, K, N, partial, splits));
+    const int64_t cnt = (int64_t)K * N;
+    f16_reduce_kernel<<<(unsigned)ceil_div(cnt, 256), 256, 0, ctx->stream>>>(partial, splits, cnt, cnt, dW, sc_x, sc_dy);
+    ctx->launches += 1;
+    PPO_CUDA(cudaGetLastError());
+    return PPO_OK;
+}
+
+int head_fwd16(ppo_ctx* ctx, const __half* H_hi, const __half* H_lo, const float* W, const float* bias, float* logits,
+               int64_t M, int K, int N, const float* sc_h) {
+    PPO_REQUIRE(N >= 1 && N <= 4 && K % 8 == 0 && (size_t)K * N * 4 <= 48 * 1024, "f16 head_fwd: needs N <= 4, K %% 8 == 0 (K=%d N=%d)", K, N);
+    int64_t blocks = ceil_div(M, 8);
+    const int64_t cap = (int64_t)ctx->num_sms * 8;
+    if (blocks > cap) blocks = cap;
+    const size_t smem = (size_t)K * N * sizeof(float);
+    switch (N) {
+        case 1: head_fwd16_kernel<1><<<(unsigned)blocks, 256, smem, ctx->stream>>>(H_hi, H_lo, W, bias, logits, M, K, sc_h); break;
+        case 2: head_fwd16_kernel<2><<<(unsigned)blocks, 256, smem, ctx->stream>>>(H_hi, H_lo, W, bias, logits, M, K, sc_h); break;
+        case 3: head_fwd16_kernel<3><<<(unsigned)blocks, 256, smem, ctx->stream>>>(H_hi, H_lo, W, bias, logits, M, K, sc_h); break;
+        default: head_fwd16_kernel<4><<<(unsigned)blocks, 256, smem, ctx->stream>>>(H_hi, H_lo, W, bias, logits, M, K, sc_h); break;
+    }
+    ctx->launches += 1;
+    PPO_CUDA(cudaGetLastError());
+    return PPO_OK;
+}
+
+int head_bwd16(ppo_ctx* ctx, const __half* H_hi, const __half* H_lo, const float* dlogits, const float* W, __half* dH_hi,
+               __half* dH_lo, float* dW, float* db, float* db_below, int64_t M, int K, int N, float slope, float* partial,
+               size_t partial_bytes, const float* sc_h, const float* sc_dh) {
+    PPO_REQUIRE(N >= 1 && N <= 4 && K % 2 == 0 && K <= 1024, "f16 head_bwd: needs N <= 4 and even K <= 1024 (K=%d N=%d)", K, N);
+    const int64_t ctas = head16_ctas(M, ctx->num_sms);
+    const int64_t rows = ceil_div(M, ctas);
+    const int64_t stride = (int64_t)K * N + N + K;
+    PPO_REQUIRE((size_t)ctas * stride * sizeof(float) <= partial_bytes, "f16 head_bwd: partial buffer too small");
+    const int kpt = (int)ceil_div(K, 512);
+    const int need_dH = dH_hi != nullptr ? 1 : 0;
+#define PPO_HEAD_BWD16(N_, Q_)                                                                                       \
+    if (N == N_ && kpt == Q_)                                                                                        \
+        head_bwd16_kernel<N_, Q_><<<(unsigned)ctas, 256, 0, ctx->stream>>>(H_hi, H_lo, dlogits, W, dH_hi, dH_lo, partial, M, \
+                                                                           K, slope, rows, need_dH, sc_h, sc_dh);
+    PPO_HEAD_BWD16(1, 1) PPO_HEAD_BWD16(1, 2) PPO_HEAD_BWD16(2, 1) PPO_HEAD_BWD16(2, 2)
+    PPO_HEAD_BWD16(3, 1) PPO_HEAD_BWD16(3, 2) PPO_HEAD_BWD16(4, 1) PPO_HEAD_BWD16(4, 2)
+#undef PPO_HEAD_BWD16
+    ctx->launches += 1;
+    PPO_CUDA(cudaGetLastError());
+    const int64_t cnt = (int64_t)K * N;
+    f16_reduce_kernel<<<(unsigned)ceil_div(cnt, 256), 256, 0, ctx->stream>>>(partial, (int)ctas, stride, cnt, dW, nullptr, nullptr);
+    f16_reduce_kernel<<<1, 256, 0, ctx->stream>>>(partial + cnt, (int)ctas, stride, N, db, nullptr, nullptr);
+    ctx->launches += 2;
+    if (db_below != nullptr && need_dH) {
+        f16_reduce_kernel<<<(unsigned)ceil_div(K, 256), 256, 0, ctx->stream>>>(partial + cnt + N, (int)ctas, stride, K, db_below, nullptr, nullptr);
+        ctx->launches += 1;
+    }
+    PPO_CUDA(cudaGetLastError());
+    return PPO_OK;
+}
+
+int ensure_f16_workspace(ppo_policy* p, int64_t tokens) {
+    F16State* st = state(p);
+    if (tokens <= st->tokens) return PPO_OK;
+    ppo_ctx* ctx = p->ctx;
+    PPO_CUDA(cudaStreamSynchronize(ctx->stream));
+    fr(st->x_hi); fr(st->x_lo); fr(st->dz_hi[0]); fr(st->dz_hi[1]); fr(st->dz_lo[0]); fr(st->dz_lo[1]); fr(st->partial);
+    for (auto& a : st->act_hi) fr(a);
+    for (auto& a : st->act_lo) fr(a);
+    const int L = p->L;
+    int hmax = 1;
+    for (int l = 1; l < L; ++l) hmax = std::max(hmax, p->dims[l]);
+    st->act_hi.assign(L + 1, nullptr);
+    st->act_lo.assign(L + 1, nullptr);
+    // +256 B of slack: the MN-major 3-D view reads whole 64-column blocks of the last row
+    const size_t slack = 256;
+    PPO_CUDA(cudaMalloc((void**)&st->x_hi, (size_t)tokens * p->dims[0] * 2 + slack));
+    PPO_CUDA(cudaMalloc((void**)&st->x_lo, (size_t)tokens * p->dims[0] * 2 + slack));
+    for (int l = 1; l < L; ++l) {
+        PPO_CUDA(cudaMalloc((void**)&st->act_hi[l], (size_t)tokens * p->dims[l] * 2 + slack));
+        PPO_CUDA(cudaMalloc((void**)&st->act_lo[l], (size_t)tokens * p->dims[l] * 2 + slack));
+    }
+    for (int i = 0; i < 2; ++i) {
+        PPO_CUDA(cudaMalloc((void**)&st->dz_hi[i], (size_t)tokens * hmax * 2 + slack));
+        PPO_CUDA(cudaMalloc((void**)&st->dz_lo[i], (size_t)tokens * hmax * 2 + slack));
+    }
+    size_t pb = 16;
+    for (int l = 0; l + 1 < L; ++l) pb = std::max(pb, f16_partial_bytes(tokens, p->dims[l], p->dims[l + 1], ctx->num_sms));
+    pb = std::max(pb, head16_partial_bytes(tokens, p->dims[L - 1], p->dims[L], ctx->num_sms));
+    PPO_CUDA(cudaMalloc((void**)&st->partial, pb));
+    st->partial_bytes = pb;
+    st->tokens = tokens;
+    return PPO_OK;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+// interface used by abi.cu
+// ---------------------------------------------------------------------------------------------
+int f16_prepare(ppo_policy* p) {
+    PPO_TRY(load_encode16());
+    const int L = p->L;
+    PPO_REQUIRE(L >= 2 && L <= F_MAX_LAYERS, "fp16-split engine: needs 2..%d Dense layers (have %d); use PPO_GEMM_FP32_SIMT",
+                F_MAX_LAYERS, L);
+    for (int l = 0; l + 1 < L; ++l) {
+        const int K = p->dims[l], N = p->dims[l + 1];
+        PPO_REQUIRE(K % 8 == 0 && N % 32 == 0 && (l == 0 || K % 32 == 0),
+                    "fp16-split engine: layer %d (%d -> %d) needs in %% 8 == 0 and hidden widths %% 32 == 0; "
+                    "use PPO_GEMM_FP32_SIMT for this policy", l, K, N);
+    }
+    PPO_REQUIRE(p->dims[L] <= 4 && p->dims[L - 1] <= 1024, "fp16-split engine: head %d -> %d needs out <= 4 and in <= 1024",
+                p->dims[L - 1], p->dims[L]);
+    if (p->f16 == nullptr) p->f16 = new F16State();
+    F16State* st = state(p);
+    if (st->layers.empty()) {
+        st->layers.resize(L);
+        for (int l = 0; l + 1 < L; ++l) {      // hidden layers only; the head has its own streaming kernels
+            const size_t n = (size_t)p->dims[l] * p->dims[l + 1] * 2;
+            F16Layer& ly = st->layers[l];
+            PPO_CUDA(cudaMalloc((void**)&ly.W_hi, n));
+            PPO_CUDA(cudaMalloc((void**)&ly.W_lo, n));
+            PPO_CUDA(cudaMalloc((void**)&ly.WT_hi, n));
+            PPO_CUDA(cudaMalloc((void**)&ly.WT_lo, n));
+        }
+        st->table.L = L;
+        for (int l = 0; l < L; ++l) {
+            st->table.K[l] = p->dims[l]; st->table.N[l] = p->dims[l + 1];
+            st->table.w_off[l] = p->w_off[l]; st->table.b_off[l] = p->b_off[l];
+        }
+        const size_t nsc = (size_t)2 * (3 * L), nst = (size_t)2 + 4 * L;
+        PPO_CUDA(cudaMalloc((void**)&st->sc, nsc * 4));
+        PPO_CUDA(cudaMalloc((void**)&st->st, nst * 4));
+        PPO_CUDA(cudaMemsetAsync(st->sc, 0, nsc * 4, p->ctx->stream));
+        PPO_CUDA(cudaMemsetAsync(st->st, 0, nst * 4, p->ctx->stream));
+    }
+    return PPO_OK;
+}
+
+int f16_refresh_weights(ppo_policy* p) {
+    F16State* st = state(p);
+    PPO_REQUIRE(st != nullptr, "fp16-split engine not prepared");
+    ppo_ctx* ctx = p->ctx;
+    const int L = p->L;
+    unsigned* wst = st->st + 2;
+    PPO_CUDA(cudaMemsetAsync(wst, 0, (size_t)4 * L * 4, ctx->stream));
+    int maxb = 1;
+    for (int l = 0; l < L; ++l) maxb = std::max(maxb, (int)(ceil_div(p->dims[l], 256) + ceil_div(p->dims[l + 1], 256)));
+    wstats_kernel<<<dim3((unsigned)maxb, (unsigned)L), 256, 0, ctx->stream>>>(p->params, st->table, wst);
+    plan_w_kernel<<<1, 32, 0, ctx->stream>>>(L, wst, st->sc);
+    ctx->launches += 2;
+    for (int l = 0; l + 1 < L; ++l) {
+        const int K = p->dims[l], N = p->dims[l + 1];
+        F16Layer& ly = st->layers[l];
+        dim3 grid((unsigned)ceil_div(N, 32), (unsigned)ceil_div(K, 32));
+        weight_prep16_kernel<<<grid, 256, 0, ctx->stream>>>(p->params + p->w_off[l], ly.W_hi, ly.W_lo, ly.WT_hi, ly.WT_lo, K, N,
+                                                            st->sc + 2 * sc_w(L, l));
+        ctx->launches += 1;
+    }
+    PPO_CUDA(cudaGetLastError());
+    return PPO_OK;
+}
+
+int f16_forward(ppo_policy* p, const float* X, int64_t M) {
+    F16State* st = state(p);
+    PPO_REQUIRE(st != nullptr, "fp16-split engine not prepared");
+    ppo_ctx* ctx = p->ctx;
+    const int L = p->L;
+    PPO_TRY(ensure_f16_workspace(p, p->ws_tokens > M ? p->ws_tokens : M));
+    PPO_TRY(launch_absmax(ctx, X, M * p->dims[0], st->st + 0));
+    plan_fwd_kernel<<<1, 32, 0, ctx->stream>>>(L, p->slope, st->st + 0, st->st + 2, st->sc);
+    ctx->launches += 1;
+    PPO_TRY(launch_split16(ctx, X, st->x_hi, st->x_lo, M * p->dims[0], st->sc + 2 * sc_act(0)));
+    for (int l = 0; l + 1 < L; ++l) {
+        const int K = p->dims[l], N = p->dims[l + 1];
+        F16Layer& ly = st->layers[l];
+        KK16Params kp{};
+        kp.epi = F_EPI_FWD; kp.act = 1; kp.slope = p->slope; kp.bias = p->params + p->b_off[l];
+        kp.sc_a = st->sc + 2 * sc_act(l); kp.sc_b = st->sc + 2 * sc_w(L, l); kp.sc_c = st->sc + 2 * sc_act(l + 1);
+        const __half* A_hi = (l == 0) ? st->x_hi : st->act_hi[l];
+        const __half* A_lo = (l == 0) ? st->x_lo : st->act_lo[l];
+        PPO_TRY(kk16_dispatch(ctx, A_hi, A_lo, ly.WT_hi, ly.WT_lo, st->act_hi[l + 1], st->act_lo[l + 1], M, N, K, kp));
+    }
+    return head_fwd16(ctx, st->act_hi[L - 1], st->act_lo[L - 1], p->params + p->w_off[L - 1], p->params + p->b_off[L - 1],
+                      p->act[L], M, p->dims[L - 1], p->dims[L], st->sc + 2 * sc_act(L - 1));
+}
+
+int f16_backward(ppo_policy* p, int64_t M) {
+    F16State* st = state(p);
+    PPO_REQUIRE(st != nullptr, "fp16-split engine not prepared");
+    ppo_ctx* ctx = p->ctx;
+    const int L = p->L;
+    PPO_REQUIRE(M <= st->tokens, "fp16-split engine: backward without a forward of the same minibatch");
+    PPO_TRY(launch_absmax(ctx, p->dlogits, M * p->dims[L], st->st + 1));
+    plan_bwd_kernel<<<1, 32, 0, ctx->stream>>>(L, p->slope, st->st + 1, st->st + 2, st->sc);
+    ctx->launches += 1;
+    int pp = 0;
+    // head: dZ_{L-2}, dW_head, db_head and db_{L-2} = colsum(dZ_{L-2})
+    PPO_TRY(head_bwd16(ctx, st->act_hi[L - 1], st->act_lo[L - 1], p->dlogits, p->params + p->w_off[L - 1], st->dz_hi[pp],
+                       st->dz_lo[pp], p->grads + p->w_off[L - 1], p->grads + p->b_off[L - 1], p->grads + p->b_off[L - 2], M,
+                       p->dims[L - 1], p->dims[L], p->slope, st->partial, st->partial_bytes, st->sc + 2 * sc_act(L - 1),
+                       st->sc + 2 * sc_dz(L, L - 2)));
+    for (int l = L - 2; l >= 0; --l) {
+        const int K = p->dims[l], N = p->dims[l + 1];
+        F16Layer& ly = st->layers[l];
+        const __half* X_hi = (l == 0) ? st->x_hi : st->act_hi[l];
+        const __half* X_lo = (l == 0) ? st->x_lo : st->act_lo[l];
+        const float* sc_dy = st->sc + 2 * sc_dz(L, l);
+        PPO_TRY(wgrad16(ctx, X_hi, X_lo, st->dz_hi[pp], st->dz_lo[pp], p->grads + p->w_off[l], st->partial, st->partial_bytes, M,
+                        K, N, st->sc + 2 * sc_act(l), sc_dy));
+        if (l > 0) {
+            KK16Params kp{};
+            kp.epi = F_EPI_DGRAD; kp.act = 0; kp.slope = p->slope; kp.gate = X_hi;
+            kp.colsum_partial = st->partial;
+            kp.sc_a = sc_dy; kp.sc_b = st->sc + 2 * sc_w(L, l); kp.sc_c = st->sc + 2 * sc_dz(L, l - 1);
+            // dX[M, K] = dY[M, N] * W[K, N]^T : A = dY (K-major in N), B = W rows (K-major in N)
+            PPO_TRY(kk16_dispatch(ctx, st->dz_hi[pp], st->dz_lo[pp], ly.W_hi, ly.W_lo, st->dz_hi[pp ^ 1], st->dz_lo[pp ^ 1], M, K, N, kp));
+            const int64_t rows = 4 * ceil_div(M, F_BM);
+            PPO_TRY(fold_colsum16(ctx, st->partial, rows, K, st->partial + (size_t)rows * K, p->grads + p->b_off[l - 1]));
+            pp ^= 1;
+        }
+    }
+    return PPO_OK;
+}
+
+void f16_destroy(ppo_policy* p) {
+    F16State* st = state(p);
+    if (!st) return;
+    for (auto& ly : st->layers) { fr(ly.W_hi); fr(ly.W_lo); fr(ly.WT_hi); fr(ly.WT_lo); }
+    fr(st->x_hi); fr(st->x_lo); fr(st->dz_hi[0]); fr(st->dz_hi[1]); fr(st->dz_lo[0]); fr(st->dz_lo[1]); fr(st->partial);
+    for (auto& a : st->act_hi) fr(a);
+    for (auto& a : st->act_lo) fr(a);
+    fr(st->sc); fr(st->st);
+    delete st;
+    p->f16 = nullptr;
+}
+
+// ---------------------------------------------------------------------------------------------
+// stand-alone entry points for tests and per-kernel benches (device pointers)
+// ---------------------------------------------------------------------------------------------
+int f16_test_operand(ppo_ctx* ctx, const float* x, __half* hi, __half* lo, int64_t n, float* sc, unsigned* st) {
+    PPO_TRY(launch_absmax(ctx, x, n, st));
+    scale_from_stat_kernel<<<1, 32, 0, ctx->stream>>>(st, sc);
+    ctx->launches += 1;
+    return launch_split16(ctx, x, hi, lo, n, sc);
+}
+int f16_test_weight(ppo_ctx* ctx, const float* W, __half* W_hi, __half* W_lo, __half* WT_hi, __half* WT_lo, int K, int N,
+                    float* sc, unsigned* st) {
+    PPO_TRY(launch_absmax(ctx, W, (int64_t)K * N, st));
+    scale_from_stat_kernel<<<1, 32, 0, ctx->stream>>>(st, sc);
+    dim3 grid((unsigned)ceil_div(N, 32), (unsigned)ceil_div(K, 32));
+    weight_prep16_kernel<<<grid, 256, 0, ctx->stream>>>(W, W_hi, W_lo, WT_hi, WT_lo, K, N, sc);
+    ctx->launches += 2;
+    PPO_CUDA(cudaGetLastError());
+    return PPO_OK;
+}
+int f16_test_set_scale(ppo_ctx* ctx, float* sc, float bound) {
+    scale_from_bound_kernel<<<1, 32, 0, ctx->stream>>>(bound, sc);
+    ctx->launches += 1;
+    PPO_CUDA(cudaGetLastError());
+    return PPO_OK;
+}
+int f16_test_fwd(ppo_ctx* ctx, const __half* X_hi, const __half* X_lo, const __half* WT_hi, const __half* WT_lo,
+                 const float* bias, __half* Y_hi, __half* Y_lo, int64_t M, int K, int N, int act, float slope,
+                 const float* sc_x, const float* sc_w, const float* sc_y) {
+    PPO_TRY(load_encode16());
+    KK16Params kp{};
+    kp.epi = F_EPI_FWD; kp.act = act; kp.slope = slope; kp.bias = bias;
+    kp.sc_a = sc_x; kp.sc_b = sc_w; kp.sc_c = sc_y;
+    return kk16_dispatch(ctx, X_hi, X_lo, WT_hi, WT_lo, Y_hi, Y_lo, M, N, K, kp);
+}
+int f16_test_dgrad(ppo_ctx* ctx, const __half* dY_hi, const __half* dY_lo, const __half* W_hi, const __half* W_lo,
+                   const __half* gate_hi, __half* dX_hi, __half* dX_lo, int64_t M, int K, int N, float slope,
+                   float* colsum_scratch, float* colsum_out, const float* sc_dy, const float* sc_w, const float* sc_dx) {
+    PPO_TRY(load_encode16());
+    KK16Params kp{};
+    kp.epi = F_EPI_DGRAD; kp.slope = slope; kp.gate = gate_hi;
+    kp.colsum_partial = colsum_out ? colsum_scratch : nullptr;
+    kp.sc_a = sc_dy; kp.sc_b = sc_w; kp.sc_c = sc_dx;
+    PPO_TRY(kk16_dispatch(ctx, dY_hi, dY_lo, W_hi, W_lo, dX_hi, dX_lo, M, K, N, kp));
+    if (colsum_out) {
+        const int64_t rows = 4 * ceil_div(M, F_BM);
+        PPO_TRY(fold_colsum16(ctx, colsum_scratch, rows, K, colsum_scratch + (size_t)rows * K, colsum_out));
+    }
+    return PPO_OK;
+}
+int f16_test_wgrad(ppo_ctx* ctx, const __half* X_hi, const __half* X_lo, const __half* dY_hi, const __half* dY_lo, float* dW,
+                   float* partial, size_t partial_bytes, int64_t M, int K, int N, const float* sc_x, const float* sc_dy) {
+    PPO_TRY(load_encode16());
+    return wgrad16(ctx, X_hi, X_lo, dY_hi, dY_lo, dW, partial, partial_bytes, M, K, N, sc_x, sc_dy);
+}
+int f16_test_join(ppo_ctx* ctx, const __half* hi, const __half* lo, int64_t n, const float* sc, float* out) {
+    join16_kernel<<<(unsigned)std::min<int64_t>(ceil_div(n, 256), (int64_t)ctx->num_sms * 16), 256, 0, ctx->stream>>>(hi, lo, n, sc, out);
+    ctx->launches += 1;
+    PPO_CUDA(cudaGetLastError());
+    return PPO_OK;
+}
+size_t f16_test_partial_bytes(ppo_ctx* ctx, int64_t M, int K, int N) { return f16_partial_bytes(M, K, N, ctx->num_sms); }
+int f16_test_head_fwd(ppo_ctx* ctx, const __half* H_hi, const __half* H_lo, const float* W, const float* bias, float* logits,
+                      int64_t M, int K, int N, const float* sc_h) {
+    return head_fwd16(ctx, H_hi, H_lo, W, bias, logits, M, K, N, sc_h);
+}
+int f16_test_head_bwd(ppo_ctx* ctx, const __half* H_hi, const __half* H_lo, const float* dlogits, const float* W,
+                      __half* dH_hi, __half* dH_lo, float* dW, float* db, float* db_below, int64_t M, int K, int N,
+                      float slope, float* partial, size_t partial_bytes, const float* sc_h, const float* sc_dh) {
+    return head_bwd16(ctx, H_hi, H_lo, dlogits, W, dH_hi, dH_lo, dW, db, db_below, M, K, N, slope, partial, partial_bytes, sc_h, sc_dh);
+}
+size_t f16_test_head_partial_bytes(int64_t M, int K, int N) { return head16_partial_bytes(M, K, N, 148); }
+
+}  // namespace ppo
