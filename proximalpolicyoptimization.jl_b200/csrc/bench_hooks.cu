@@ -2,6 +2,7 @@
 // device-resident problem (CUDA events on the ctx stream, optional L2 flush between launches).
 // Used by bench.py for the per-kernel roofline numbers; not part of the reference-facing API.
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -82,7 +83,9 @@ template <typename F>
 int time_loop(ppo_ctx* ctx, Scope& sc, int iters, int flush, F&& launch, double* ms_out) {
     PPO_CUDA(cudaEventCreate(&sc.e0));
     PPO_CUDA(cudaEventCreate(&sc.e1));
-    for (int w = 0; w < 3; ++w) PPO_TRY(launch());
+    const char* wenv = getenv("PPO_BENCH_WARMUP");          // profiling runs set 0 so that ncu sees one launch per kernel
+    const int warm = wenv ? atoi(wenv) : 3;
+    for (int w = 0; w < warm; ++w) PPO_TRY(launch());
     PPO_CUDA(cudaStreamSynchronize(ctx->stream));
     double total = 0.0;
     for (int it = 0; it < iters; ++it) {
@@ -265,7 +268,8 @@ extern "C" int ppo_bench_kernel(ppo_ctx* ctx, const char* which, int64_t n, int 
         const int64_t M = n; const int K = a, N = b;
         float *X, *W, *bias, *Y, *dW, *db, *part, *sc_, *lg;
         __half *Xh, *Xl, *Wh, *Wl, *WTh, *WTl, *Yh, *Yl, *dXh, *dXl;
-        unsigned* st;
+        unsigned *st, *sgn;
+        PPO_TRY(sc.alloc(&sgn, std::max(f16_test_sign_words(M, (K + 31) / 32 * 32), f16_test_sign_words(M, (N + 31) / 32 * 32)) + 64));
         PPO_TRY(sc.alloc(&X, (size_t)std::max<int64_t>(M * K, M * N))); PPO_TRY(sc.alloc(&W, (size_t)K * N));
         PPO_TRY(sc.alloc(&bias, (size_t)std::max(K, N))); PPO_TRY(sc.alloc(&Y, (size_t)M * N));
         PPO_TRY(sc.alloc(&Xh, (size_t)M * K + 128)); PPO_TRY(sc.alloc(&Xl, (size_t)M * K + 128));
@@ -283,6 +287,8 @@ extern "C" int ppo_bench_kernel(ppo_ctx* ctx, const char* which, int64_t n, int 
         float *sX = sc_, *sW = sc_ + 2, *sY = sc_ + 4, *sO = sc_ + 6;
         PPO_TRY(f16_test_operand(ctx, X, Xh, Xl, M * K, sX, st));
         PPO_TRY(f16_test_operand(ctx, Y, Yh, Yl, M * N, sY, st));
+        PPO_REQUIRE(K % 32 == 0 || w != "tc3_dgrad", "bench f16: K %% 32 for dgrad");
+        if (K % 32 == 0) PPO_TRY(f16_test_signbits(ctx, X, M, K, sgn));
         if (w == "head16_fwd" || w == "head16_bwd") {
             PPO_REQUIRE(N <= 4, "bench head16: N <= 4");
             PPO_TRY(fill(ctx, lg, M * N, 0, 1, 5));
@@ -302,11 +308,11 @@ extern "C" int ppo_bench_kernel(ppo_ctx* ctx, const char* which, int64_t n, int 
         if (w == "tc3_fwd") {
             PPO_TRY(f16_test_set_scale(ctx, sO, (float)K + 1.0f));
             PPO_TRY(time_loop(ctx, sc, iters, flush_l2_flag,
-                              [&]() { return f16_test_fwd(ctx, Xh, Xl, WTh, WTl, bias, Yh, Yl, M, K, N, 1, 0.01f, sX, sW, sO); }, ms_out));
+                              [&]() { return f16_test_fwd(ctx, Xh, Xl, WTh, WTl, bias, Yh, Yl, sgn, M, K, N, 1, 0.01f, sX, sW, sO); }, ms_out));
         } else if (w == "tc3_dgrad") {
             PPO_TRY(f16_test_set_scale(ctx, sO, (float)N));
             PPO_TRY(time_loop(ctx, sc, iters, flush_l2_flag,
-                              [&]() { return f16_test_dgrad(ctx, Yh, Yl, Wh, Wl, Xh, dXh, dXl, M, K, N, 0.01f, part, db, sY, sW, sO); }, ms_out));
+                              [&]() { return f16_test_dgrad(ctx, Yh, Yl, Wh, Wl, sgn, dXh, dXl, M, K, N, 0.01f, part, db, sY, sW, sO); }, ms_out));
         } else {
             PPO_TRY(time_loop(ctx, sc, iters, flush_l2_flag,
                               [&]() { return f16_test_wgrad(ctx, Xh, Xl, Yh, Yl, dW, part, pb, M, K, N, sX, sY); }, ms_out));
@@ -381,14 +387,17 @@ extern "C" int ppo_dense_op(ppo_ctx* ctx, int mode, int op, int64_t M, int K, in
         }
         if (op == 0) {
             PPO_TRY(f16_test_set_scale(ctx, sO, (float)((xmax * colmax + bmax) * 1.001)));
-            PPO_TRY(f16_test_fwd(ctx, Xh, Xl, WTh, WTl, dB, Oh, Ol, M, K, N, act ? 1 : 0, slope, sX, sW, sO));
+            PPO_TRY(f16_test_fwd(ctx, Xh, Xl, WTh, WTl, dB, Oh, Ol, nullptr, M, K, N, act ? 1 : 0, slope, sX, sW, sO));
             PPO_TRY(f16_test_join(ctx, Oh, Ol, (int64_t)out_elems, sO, dOut));
         } else if (op == 1) {
             float *cs_scratch, *cs_out;
             PPO_TRY(sc.alloc((char**)&cs_scratch, f16_test_partial_bytes(ctx, M, K, N)));
             PPO_TRY(sc.alloc(&cs_out, (size_t)K));
             PPO_TRY(f16_test_set_scale(ctx, sO, (float)(dymax * rowmax * 1.001)));
-            PPO_TRY(f16_test_dgrad(ctx, DYh, DYl, Wh, Wl, Xh, Oh, Ol, M, K, N, slope, cs_scratch, cs_out, sDY, sW, sO));
+            unsigned* gate;
+            PPO_TRY(sc.alloc(&gate, f16_test_sign_words(M, K) + 64));
+            PPO_TRY(f16_test_signbits(ctx, dXp, M, K, gate));
+            PPO_TRY(f16_test_dgrad(ctx, DYh, DYl, Wh, Wl, gate, Oh, Ol, M, K, N, slope, cs_scratch, cs_out, sDY, sW, sO));
             PPO_TRY(f16_test_join(ctx, Oh, Ol, (int64_t)out_elems, sO, dOut));
             if (out2) PPO_CUDA(cudaMemcpyAsync(out2, cs_out, (size_t)K * 4, cudaMemcpyDeviceToHost, s));
         } else {

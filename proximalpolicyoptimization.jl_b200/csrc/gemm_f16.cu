@@ -32,6 +32,8 @@
 #include <cuda.h>
 #include <cuda_fp16.h>
 
+#include <stdlib.h>
+
 #include <algorithm>
 
 #include "gemm_f16.cuh"
@@ -44,9 +46,21 @@ namespace {
 constexpr int F_BM = 128;
 constexpr int F_BK = 64;                    // 64 fp16 = one 128-byte swizzle row
 constexpr int F_STAGES = 2;
-constexpr int F_CHUNK_KB = 2;               // k-blocks per TMEM accumulation chain (128 elements = 24 MMAs)
-constexpr int F_EPI_THREADS = 256;          // 8 epilogue warps: 4 lane quarters x 2 column halves
+constexpr int F_CHUNK_KB = 2;               // mn kernel: k-blocks per TMEM accumulation chain (128 elements = 24 MMAs)
+// kk kernel: 256 elements = 48 MMAs per chain.  The two TMEM stages then hold a whole K = 512 tile of look-ahead, so
+// the MMA issuer keeps running while the epilogue warps finish the previous tile (with 128-element chains the tensor
+// pipe idled ~45 % of the time waiting for them: profiles/r01_f16_ncu.md).  The longer chain's round-toward-zero
+// deficit is removed by the compensated fold (KK16Params::rz_comp): measured gradient error vs fp64 4-5e-6 of each
+// tensor's max-abs (fp32 FFMA engine: 2-4e-6; 128-element chains without compensation: 5-6e-6).
+constexpr int F_KK_CHUNK_KB = 4;
+// calibrated on the C3-width policy gradient (scripts/f16_matrix.sh): the scale bias of the gradient against the fp64
+// oracle crosses zero at 1.3e-8 .. 1.7e-8 per MMA for 128- and 256-element chains alike (theory for an fp32 adder that
+// truncates every add: 0.72 * 2^-24 / 2 = 2.1e-8)
+constexpr float F_RZ_COMP = 1.5e-8f;
+constexpr int F_EPI_THREADS = 256;          // mn kernel: 8 epilogue warps = 4 lane quarters x 2 column halves
 constexpr int F_THREADS = 64 + F_EPI_THREADS;
+constexpr int F_KK_EPI_THREADS = 512;       // kk kernel: 16 epilogue warps = 4 lane quarters x 4 column quarters (the
+constexpr int F_KK_THREADS = 64 + F_KK_EPI_THREADS;   // per-element epilogue is issue/latency bound: more warps, fewer columns each)
 constexpr int FA_TILE_BYTES = F_BM * F_BK * 2;   // 16 KB
 constexpr int F_MAX_LAYERS = 8;
 constexpr int F_EXP_TARGET = 14;            // bound * 2^e <= 2^14 (fp16 max is ~2^16)
@@ -62,11 +76,13 @@ __device__ __forceinline__ void f16_split(float a, __half& hi, __half& lo) {
     hi = __float2half_rn(a);
     lo = __float2half_rn(a - __half2float(hi));
 }
-// the same, but a strictly positive value never loses its sign to underflow (the backward pass gates on sign(hi))
-__device__ __forceinline__ void f16_split_keep_sign(float a, __half& hi, __half& lo) {
-    hi = __float2half_rn(a);
-    if (a > 0.0f && __half_as_ushort(hi) == 0) hi = __ushort_as_half((unsigned short)1);
-    lo = __float2half_rn(a - __half2float(hi));
+// two elements at once (cvt.rn.f16x2.f32): returns the packed hi pair and lo pair
+__device__ __forceinline__ void f16_split2(float a, float b, uint32_t& hi, uint32_t& lo) {
+    const __half2 h = __floats2half2_rn(a, b);
+    const float2 hf = __half22float2(h);
+    const __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    lo = *reinterpret_cast<const uint32_t*>(&l);
 }
 __device__ __forceinline__ void unpack8(const uint4& q, float* x) {
     const __half2* h = reinterpret_cast<const __half2*>(&q);
@@ -77,6 +93,13 @@ __device__ __forceinline__ void unpack8(const uint4& q, float* x) {
     }
 }
 
+// sign-bit words of an activation [M][N]: tiled so that the 32 rows a warp owns are contiguous (coalesced 128-byte
+// stores / loads from the row-per-thread epilogues): word (row, w) lives at ((row / 128) * (N / 32) + w) * 128 + row % 128
+__host__ __device__ inline size_t sign_index(int64_t row, int w, int nwords) {
+    return ((size_t)(row >> 7) * nwords + w) * 128 + (size_t)(row & 127);
+}
+inline size_t sign_words(int64_t rows, int N) { return (size_t)ceil_div(rows, 128) * 128 * (N / 32); }
+
 struct KK16Params {
     int M, N, K;
     int tiles_m, tiles_n, k_blocks;
@@ -84,31 +107,54 @@ struct KK16Params {
     int act;                 // fwd: apply leakyrelu
     float slope;
     const float* bias;       // fwd
-    const __half* gate;      // dgrad: hi half of the activation whose sign gates the gradient, [M][N]
+    const uint32_t* gate;    // dgrad: sign bits of the activation that gates the gradient (bit = act > 0), sign_index layout
+    uint32_t* signs_out;     // fwd: sign bits of the output activation (rows padded to a multiple of 128)
     float* colsum_partial;   // dgrad: [tiles_m][4][N] column sums of the (unscaled) output per 32-row quarter
     const float* sc_a;       // {scale, 1/scale} of the A operand
     const float* sc_b;
     const float* sc_c;       // of the output
+    int chunk_kb;            // k-blocks per TMEM accumulation chain
+    // The tensor core adds each MMA result into its fp32 accumulator with round-toward-zero: every add loses on average
+    // ~0.72 * 2^-24 of the running sum, always towards zero, so a chain of n MMAs comes out short by ~ n/2 of that (the
+    // running sum grows along the chain).  The fold multiplies each finished chain by 1 + rz_comp * n to remove this
+    // systematic part (the random part stays); 0 disables it.
+    float rz_comp;
 };
 
 template <int BN>
 struct KK16Smem {
     static constexpr int B_TILE_BYTES = BN * F_BK * 2;
     static constexpr int STAGE_BYTES = 2 * FA_TILE_BYTES + 2 * B_TILE_BYTES;
-    // 4 independent store groups (row half x column half, 2 warps each); each stages 64 rows x 32 columns
-    // of hi and of lo (2 x 4 KB) for its own TMA stores
-    static constexpr int STAGING_BYTES = 4 * 2 * 64 * 32 * 2;
-    static constexpr int TOTAL = F_STAGES * STAGE_BYTES + STAGING_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+    static constexpr int NST = BN > 128 ? 2 : 3;        // operand pipeline stages (96 KB / 64 KB each)
+    static constexpr int NACC = BN > 128 ? 2 : 4;       // TMEM accumulator stages (all 512 columns in use)
+    // every epilogue warp stages its own 32 rows x 16 columns of hi and of lo (2 x 1 KB) and issues its own TMA
+    // stores: no cross-warp barrier in the epilogue, and the hi / lo buffers alternate so that a store's smem read
+    // overlaps the conversion of the other half
+    static constexpr int STAGING_BYTES = 16 * 2 * 32 * 16 * 2;
+    static constexpr int TOTAL = NST * STAGE_BYTES + STAGING_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 };
 
+// 16 columns per TMEM load: the 16-warp kk epilogue runs at 96 registers per thread
+// `comp` compensates the tensor core's round-toward-zero accumulation (see KK16Params::rz_comp)
 template <int CPT>
-__device__ __forceinline__ void drain_chunk16(uint32_t taddr, float* s) {
+__device__ __forceinline__ void drain_chunk16_narrow(uint32_t taddr, float* s, float comp) {
+#pragma unroll
+    for (int c = 0; c < CPT / 16; ++c) {
+        float v[16];
+        tmem_ld16(taddr + (uint32_t)(c * 16), v);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) s[c * 16 + j] = fmaf(v[j], comp, s[c * 16 + j]);
+    }
+}
+
+template <int CPT>
+__device__ __forceinline__ void drain_chunk16(uint32_t taddr, float* s, float comp) {
 #pragma unroll
     for (int c4 = 0; c4 < CPT / 32; ++c4) {
         float v[32];
         tmem_ld32(taddr + (uint32_t)(c4 * 32), v);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) s[c4 * 32 + j] += v[j];
+        for (int j = 0; j < 32; ++j) s[c4 * 32 + j] = fmaf(v[j], comp, s[c4 * 32 + j]);
     }
 }
 
@@ -142,35 +188,36 @@ __device__ __forceinline__ void colsum16(const float* v, int lane, float& out, i
 }
 
 template <int BN>
-__global__ void __launch_bounds__(F_THREADS, 1)
+__global__ void __launch_bounds__(F_KK_THREADS, 1)
 f16_gemm_kk_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                    const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
                    const __grid_constant__ CUtensorMap tmC_hi, const __grid_constant__ CUtensorMap tmC_lo,
                    const KK16Params p) {
     using S = KK16Smem<BN>;
-    constexpr int CPT = BN / 2;   // columns per epilogue thread
+    constexpr int CPT = BN / 4;   // columns per epilogue thread
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    unsigned char* staging = smem + F_STAGES * S::STAGE_BYTES;
+    constexpr int NST = S::NST, NACC = S::NACC;
+    unsigned char* staging = smem + NST * S::STAGE_BYTES;
     uint64_t* bars = reinterpret_cast<uint64_t*>(staging + S::STAGING_BYTES);
-    uint64_t* full = bars;                    // [F_STAGES]
-    uint64_t* empty = bars + F_STAGES;        // [F_STAGES]
-    uint64_t* tfull = bars + 2 * F_STAGES;    // [2]
-    uint64_t* tempty = tfull + 2;             // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+    uint64_t* full = bars;                    // [NST]
+    uint64_t* empty = bars + NST;             // [NST]
+    uint64_t* tfull = bars + 2 * NST;         // [NACC]
+    uint64_t* tempty = tfull + NACC;          // [NACC]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + NACC);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int num_tiles = p.tiles_m * p.tiles_n;
-    const int chunks_per_tile = (p.k_blocks + F_CHUNK_KB - 1) / F_CHUNK_KB;
+    const int chunks_per_tile = (p.k_blocks + p.chunk_kb - 1) / p.chunk_kb;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < F_STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(tfull + a, 1); mbar_init(tempty + a, F_EPI_THREADS); }
+        for (int s = 0; s < NST; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+        for (int a = 0; a < NACC; ++a) { mbar_init(tfull + a, 1); mbar_init(tempty + a, F_KK_EPI_THREADS); }
         fence_barrier_init();
         tma_prefetch_desc(&tmA_hi); tma_prefetch_desc(&tmA_lo); tma_prefetch_desc(&tmB_hi); tma_prefetch_desc(&tmB_lo);
         tma_prefetch_desc(&tmC_hi); tma_prefetch_desc(&tmC_lo);
     }
-    if (warp == 1) tmem_alloc(tmem_slot, 2 * BN);
+    if (warp == 1) tmem_alloc(tmem_slot, NACC * BN);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -191,7 +238,7 @@ f16_gemm_kk_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
                     tma_load_2d(st + FA_TILE_BYTES, &tmA_lo, k0, m0, full + stage);
                     tma_load_2d(st + 2 * FA_TILE_BYTES, &tmB_hi, k0, n0, full + stage);
                     tma_load_2d(st + 2 * FA_TILE_BYTES + S::B_TILE_BYTES, &tmB_lo, k0, n0, full + stage);
-                    if (++stage == F_STAGES) { stage = 0; phase ^= 1; }
+                    if (++stage == NST) { stage = 0; phase ^= 1; }
                 }
             }
         }
@@ -203,11 +250,11 @@ f16_gemm_kk_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
             uint32_t cc = 0;   // accumulation chains issued so far
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
                 for (int kb = 0; kb < p.k_blocks; ++cc) {
-                    const int acc = (int)(cc & 1u);
-                    mbar_wait(tempty + acc, ((cc >> 1) & 1u) ^ 1u);
+                    const int acc = (int)(cc % (uint32_t)NACC);
+                    mbar_wait(tempty + acc, ((cc / (uint32_t)NACC) & 1u) ^ 1u);
                     tc_fence_after();
                     const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
-                    const int kb_end = kb + F_CHUNK_KB < p.k_blocks ? kb + F_CHUNK_KB : p.k_blocks;
+                    const int kb_end = kb + p.chunk_kb < p.k_blocks ? kb + p.chunk_kb : p.k_blocks;
                     for (int kc = 0; kb < kb_end; ++kb, ++kc) {
                         mbar_wait(full + stage, phase);
                         tc_fence_after();
@@ -225,23 +272,19 @@ f16_gemm_kk_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
                         }
                         tc_commit(empty + stage);            // frees the smem slot when these MMAs retire
                         if (kb == kb_end - 1) tc_commit(tfull + acc);
-                        if (++stage == F_STAGES) { stage = 0; phase ^= 1; }
+                        if (++stage == NST) { stage = 0; phase ^= 1; }
                     }
                 }
             }
         }
     } else {
-        // ===================== epilogue: 8 warps = 4 lane quarters x 2 column halves =====================
+        // ===================== epilogue: 16 warps = 4 lane quarters x 4 column quarters =====================
         const int q = warp & 3;                        // TMEM lane quarter this warp may access
-        const int half = (warp - 2) >> 2;              // which BN/2 columns
+        const int cq = (warp - 2) >> 2;                // which BN/4 columns
         const int row_in_tile = q * 32 + lane;
-        // store group = (row half, column half): two warps, 64 rows x CPT columns, own staging + own TMA stores
-        const int rh = q >> 1;
-        const int grp = rh * 2 + half;
-        const int rg = (q & 1) * 32 + lane;            // row within the group's 64 rows
-        uint4* st_hi = reinterpret_cast<uint4*>(staging + grp * 8192);
-        uint4* st_lo = st_hi + 64 * 4;                 // + 4096 B
-        const bool storer = ((q & 1) == 0) && lane == 0;
+        uint4* st_hi = reinterpret_cast<uint4*>(staging + (warp - 2) * 2048);
+        uint4* st_lo = st_hi + 32 * 2;                 // + 1024 B
+        const int swz = (lane >> 2) & 1;               // SWIZZLE_32B: 16-byte chunk c of row r goes to chunk c ^ ((r >> 2) & 1)
         const float unscale = __ldg(p.sc_a + 1) * __ldg(p.sc_b + 1);
         const float cscale = __ldg(p.sc_c);
         uint32_t cc = 0;
@@ -251,97 +294,103 @@ f16_gemm_kk_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
             float s[CPT];
 #pragma unroll
             for (int j = 0; j < CPT; ++j) s[j] = 0.0f;
-            if (p.epi == F_EPI_DGRAD && row < p.M) {
-                // the gate values are needed only after the whole contraction: pull their lines towards the SM now
-                const char* gp = reinterpret_cast<const char*>(p.gate + (size_t)row * p.N + n0 + half * CPT);
+            // dgrad: this thread's gate bits (one word per 32 columns), fetched before the contraction finishes
+            uint32_t gbits[CPT / 32];
+            if (p.epi == F_EPI_DGRAD) {
 #pragma unroll
-                for (int l = 0; l < CPT * 2 / 128; ++l)
-                    if (n0 + half * CPT + l * 64 < p.N) asm volatile("prefetch.global.L2 [%0];" ::"l"(gp + l * 128));
+                for (int g = 0; g < CPT / 32; ++g) {
+                    const int col0 = n0 + cq * CPT + g * 32;
+                    gbits[g] = (row < p.M && col0 < p.N) ? __ldg(p.gate + sign_index(row, col0 >> 5, p.N >> 5)) : 0u;
+                }
             }
             for (int ch = 0; ch < chunks_per_tile; ++ch, ++cc) {
-                const int acc = (int)(cc & 1u);
-                mbar_wait(tfull + acc, (cc >> 1) & 1u);
+                const int acc = (int)(cc % (uint32_t)NACC);
+                mbar_wait(tfull + acc, (cc / (uint32_t)NACC) & 1u);
                 tc_fence_after();
-                drain_chunk16<CPT>(tmem_base + (uint32_t)(acc * BN + half * CPT) + ((uint32_t)(q * 32) << 16), s);
+                const int kb_in_chunk = (ch + 1) * p.chunk_kb <= p.k_blocks ? p.chunk_kb : p.k_blocks - ch * p.chunk_kb;
+                drain_chunk16_narrow<CPT>(tmem_base + (uint32_t)(acc * BN + cq * CPT) + ((uint32_t)(q * 32) << 16), s,
+                                          1.0f + p.rz_comp * (float)(3 * (F_BK / 16) * kb_in_chunk));
                 tc_fence_before();
                 mbar_arrive(tempty + acc);
             }
-            // ---- unscale, bias / activation (or gradient gate), rescale, fp16 split, staged TMA store (32 columns at a time)
+            // ---- unscale, bias / activation (or gradient gate), rescale, fp16 split, staged TMA store (16 columns at a time)
 #pragma unroll
             for (int g = 0; g < CPT / 32; ++g) {
-                const int col0 = n0 + half * CPT + g * 32;
+                const int col0 = n0 + cq * CPT + g * 32;
                 float* v = s + g * 32;
                 if (p.epi == F_EPI_FWD) {
+                    uint32_t w = 0u;
+                    const bool full = (p.bias != nullptr) && (col0 + 32 <= p.N);
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const int col = col0 + j;
-                        const float x = fmaf(v[j], unscale, (p.bias != nullptr && col < p.N) ? __ldg(p.bias + col) : 0.0f);
-                        v[j] = (p.act && !(x > 0.0f)) ? p.slope * x : x;
-                    }
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] *= unscale;
-                    if (row < p.M && col0 + 32 <= p.N) {
-                        const uint4* gp = reinterpret_cast<const uint4*>(p.gate + (size_t)row * p.N + col0);
-#pragma unroll
-                        for (int j8 = 0; j8 < 4; ++j8) {
-                            const uint4 hq = __ldg(gp + j8);
-                            float h[8];
-                            unpack8(hq, h);
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) v[8 * j8 + j] = (h[j] > 0.0f) ? v[8 * j8 + j] : p.slope * v[8 * j8 + j];
+                    for (int j4 = 0; j4 < 8; ++j4) {
+                        float4 b4 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                        if (full) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0) + j4);
+                        else if (p.bias != nullptr) {
+                            const int c = col0 + 4 * j4;
+                            if (c < p.N) b4.x = __ldg(p.bias + c);
+                            if (c + 1 < p.N) b4.y = __ldg(p.bias + c + 1);
+                            if (c + 2 < p.N) b4.z = __ldg(p.bias + c + 2);
+                            if (c + 3 < p.N) b4.w = __ldg(p.bias + c + 3);
                         }
-                    } else if (row < p.M) {
+                        const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                            if (col0 + j < p.N) {
-                                const float h = __half2float(p.gate[(size_t)row * p.N + col0 + j]);
-                                v[j] = (h > 0.0f) ? v[j] : p.slope * v[j];
-                            }
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] = 0.0f;     // rows beyond M: keep them out of the column sums
+                        for (int i = 0; i < 4; ++i) {
+                            const int j = 4 * j4 + i;
+                            const float x = fmaf(v[j], unscale, bb[i]);
+                            const bool pos = x > 0.0f;
+                            w |= (pos ? 1u : 0u) << j;
+                            v[j] = (p.act && !pos) ? p.slope * x : x;
+                        }
                     }
-                }
-                if (p.colsum_partial != nullptr) {
-                    // = the bias gradient of the layer below, fused here so that dX is never re-read for it
+                    if (p.signs_out != nullptr && col0 < p.N) p.signs_out[sign_index(row, col0 >> 5, p.N >> 5)] = w;
+                } else {
+                    const float inb = (row < p.M) ? unscale : 0.0f;     // rows beyond M: keep them out of the column sums
+                    const float ins = inb * p.slope;
+                    const uint32_t w = gbits[g];
 #pragma unroll
-                    for (int hh = 0; hh < 2; ++hh) {
+                    for (int j = 0; j < 32; ++j) v[j] *= ((w >> j) & 1u) ? inb : ins;
+                }
+#pragma unroll
+                for (int hh = 0; hh < 2; ++hh) {
+                    float* vv = v + 16 * hh;
+                    if (p.colsum_partial != nullptr) {
+                        // = the bias gradient of the layer below, fused here so that dX is never re-read for it
                         float cs; int cidx;
-                        colsum16(v + 16 * hh, lane, cs, cidx);
+                        colsum16(vv, lane, cs, cidx);
                         if ((lane & 1) == 0 && col0 + 16 * hh + cidx < p.N)
                             p.colsum_partial[((size_t)(tile / p.tiles_n) * 4 + q) * p.N + col0 + 16 * hh + cidx] = cs;
                     }
-                }
-                if (storer) bulk_wait_read0();        // the group's previous TMA stores have read its staging tile
-                named_bar_sync(1 + grp, 64);
-                // 64-byte rows, SWIZZLE_64B: 16-byte chunk j8 of row r goes to chunk j8 ^ ((r >> 1) & 3)
+                    uint4 h[2], l[2];
 #pragma unroll
-                for (int j8 = 0; j8 < 4; ++j8) {
-                    __half h[8], l[8];
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        if (p.epi == F_EPI_FWD) f16_split_keep_sign(v[8 * j8 + j] * cscale, h[j], l[j]);
-                        else f16_split(v[8 * j8 + j] * cscale, h[j], l[j]);
+                    for (int j8 = 0; j8 < 2; ++j8) {
+                        f16_split2(vv[8 * j8 + 0] * cscale, vv[8 * j8 + 1] * cscale, h[j8].x, l[j8].x);
+                        f16_split2(vv[8 * j8 + 2] * cscale, vv[8 * j8 + 3] * cscale, h[j8].y, l[j8].y);
+                        f16_split2(vv[8 * j8 + 4] * cscale, vv[8 * j8 + 5] * cscale, h[j8].z, l[j8].z);
+                        f16_split2(vv[8 * j8 + 6] * cscale, vv[8 * j8 + 7] * cscale, h[j8].w, l[j8].w);
                     }
-                    const int sw = j8 ^ ((rg >> 1) & 3);
-                    st_hi[rg * 4 + sw] = make_uint4(pack_h2(h[0], h[1]), pack_h2(h[2], h[3]), pack_h2(h[4], h[5]), pack_h2(h[6], h[7]));
-                    st_lo[rg * 4 + sw] = make_uint4(pack_h2(l[0], l[1]), pack_h2(l[2], l[3]), pack_h2(l[4], l[5]), pack_h2(l[6], l[7]));
-                }
-                fence_proxy_async_smem();
-                named_bar_sync(1 + grp, 64);
-                if (storer) {
-                    tma_store_2d(&tmC_hi, st_hi, col0, m0 + rh * 64);
-                    tma_store_2d(&tmC_lo, st_lo, col0, m0 + rh * 64);
-                    bulk_commit();
+                    // hi: wait until the previous hi store has read its buffer (the lo store issued after it may still run)
+                    if (lane == 0) bulk_wait_read1();
+                    __syncwarp();
+                    st_hi[lane * 2 + (0 ^ swz)] = h[0];
+                    st_hi[lane * 2 + (1 ^ swz)] = h[1];
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) { tma_store_2d(&tmC_hi, st_hi, col0 + 16 * hh, m0 + q * 32); bulk_commit(); }
+                    if (lane == 0) bulk_wait_read1();
+                    __syncwarp();
+                    st_lo[lane * 2 + (0 ^ swz)] = l[0];
+                    st_lo[lane * 2 + (1 ^ swz)] = l[1];
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) { tma_store_2d(&tmC_lo, st_lo, col0 + 16 * hh, m0 + q * 32); bulk_commit(); }
                 }
             }
         }
-        if (storer) bulk_wait_all0();
+        if (lane == 0) bulk_wait_all0();
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem_base, 2 * BN);
+    if (warp == 1) tmem_dealloc(tmem_base, NACC * BN);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -457,7 +506,9 @@ f16_gemm_mn_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
             const int acc = (int)(cc & 1u);
             mbar_wait(tfull + acc, (cc >> 1) & 1u);
             tc_fence_after();
-            drain_chunk16<CPT>(tmem_base + (uint32_t)(acc * BN + half * CPT) + ((uint32_t)(q * 32) << 16), s);
+            const int kb_in_chunk = ((int)cc + 1) * F_CHUNK_KB <= k_blocks ? F_CHUNK_KB : k_blocks - (int)cc * F_CHUNK_KB;
+            drain_chunk16<CPT>(tmem_base + (uint32_t)(acc * BN + half * CPT) + ((uint32_t)(q * 32) << 16), s,
+                               1.0f + F_RZ_COMP * (float)(3 * (F_BK / 16) * kb_in_chunk));
             tc_fence_before();
             mbar_arrive(tempty + acc);
         }
@@ -635,6 +686,19 @@ join16_kernel(const __half* __restrict__ hi, const __half* __restrict__ lo, int6
         out[i] = (__half2float(hi[i]) + __half2float(lo[i])) * inv;
 }
 
+// sign bits of an fp32 matrix [M][N] (N % 32 == 0) in the sign_index layout (tests / benches build gates with it)
+__global__ void __launch_bounds__(256)
+signbits_kernel(const float* __restrict__ x, int64_t M, int N, uint32_t* __restrict__ out) {
+    const int nw = N >> 5;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < M * nw; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t row = i / nw;
+        const int w = (int)(i % nw);
+        uint32_t b = 0u;
+        for (int j = 0; j < 32; ++j) b |= (x[row * N + w * 32 + j] > 0.0f ? 1u : 0u) << j;
+        out[sign_index(row, w, nw)] = b;
+    }
+}
+
 // W[K][N] * scale -> hi/lo of W and of W^T[N][K]
 __global__ void __launch_bounds__(256)
 weight_prep16_kernel(const float* __restrict__ W, __half* __restrict__ W_hi, __half* __restrict__ W_lo,
@@ -753,102 +817,112 @@ head_fwd16_kernel(const __half* __restrict__ H_hi, const __half* __restrict__ H_
 
 // One pass over H (fp16 pair): dH = (dlogits W^T) .* leakyrelu'(H) written as a scaled fp16 pair; per-CTA partials
 // of dW[k][n], db[n] and of the column sums of dH (= the bias gradient of the layer below).
-// Partial layout per CTA: [K*N dW][N db][K colsum(dH)].  Thread t owns the column pairs 2 (t + 256 q), q < KPT.
-template <int N, int KPT>
-__global__ void __launch_bounds__(256)
-head_bwd16_kernel(const __half* __restrict__ H_hi, const __half* __restrict__ H_lo, const float* __restrict__ dlogits,
-                  const float* __restrict__ W, __half* __restrict__ dH_hi, __half* __restrict__ dH_lo,
+// Partial layout per CTA: [K*N dW][N db][K colsum(dH)].  A thread owns 4 consecutive columns (8-byte loads and
+// stores); K/4 threads cover a row, so a CTA walks 256 / (K/4) rows at once, RU of them in flight per thread.
+template <int N>
+__global__ void __launch_bounds__(256, 2)
+head_bwd16_kernel(const __half* __restrict__ H_hi, const __half* __restrict__ H_lo,
+                  const float* __restrict__ dlogits, const float* __restrict__ W, __half* __restrict__ dH_hi, __half* __restrict__ dH_lo,
                   float* __restrict__ partial, int64_t M, int K, float slope, int64_t rows_per_cta, int need_dH,
                   const float* sc_h, const float* sc_dh) {
+    extern __shared__ float red[];                     // [rpp][K*N + N + K]
     const int tid = threadIdx.x;
+    const int TPR = K >> 2;
+    const int rpp = 256 / TPR;
+    const int rg = tid / TPR, ct = tid - rg * TPR;
+    const bool active = rg < rpp;
+    const int k = 4 * ct;
     const float inv_h = __ldg(sc_h + 1);
     const float s_dh = need_dH ? __ldg(sc_dh) : 1.0f;
-    float w[KPT][2][N], aw[KPT][2][N], ab[N], cs[KPT][2];
+    float w[4][N], aw[4][N], ab[N], cs[4];
 #pragma unroll
-    for (int q = 0; q < KPT; ++q)
+    for (int c = 0; c < 4; ++c) {
+        cs[c] = 0.0f;
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
-            cs[q][c] = 0.0f;
-            const int k = 2 * (tid + q * 256) + c;
-#pragma unroll
-            for (int n = 0; n < N; ++n) {
-                w[q][c][n] = (k < K) ? W[k * N + n] : 0.0f;
-                aw[q][c][n] = 0.0f;
-            }
+        for (int n = 0; n < N; ++n) {
+            w[c][n] = active ? W[(k + c) * N + n] : 0.0f;
+            aw[c][n] = 0.0f;
         }
+    }
 #pragma unroll
     for (int n = 0; n < N; ++n) ab[n] = 0.0f;
     const int64_t r0 = (int64_t)blockIdx.x * rows_per_cta;
     const int64_t r1 = r0 + rows_per_cta < M ? r0 + rows_per_cta : M;
-    constexpr int RU = 4;
-    for (int64_t m = r0; m < r1; m += RU) {
-        __half2 hh[RU][KPT], hl[RU][KPT];
+    constexpr int RU = 6;
+    for (int64_t m = r0 + rg; m < r1 && active; m += (int64_t)RU * rpp) {
+        uint2 hh[RU], hl[RU];
         float d[RU][N];
 #pragma unroll
         for (int u = 0; u < RU; ++u) {
-            const bool rv = m + u < r1;
-#pragma unroll
-            for (int q = 0; q < KPT; ++q) {
-                const int k = 2 * (tid + q * 256);
-                uint32_t a = 0u, b = 0u;
-                if (rv && k < K) {
-                    a = __ldcs(reinterpret_cast<const unsigned int*>(H_hi + (m + u) * K + k));
-                    b = __ldcs(reinterpret_cast<const unsigned int*>(H_lo + (m + u) * K + k));
-                }
-                hh[u][q] = *reinterpret_cast<__half2*>(&a);
-                hl[u][q] = *reinterpret_cast<__half2*>(&b);
+            const int64_t row = m + (int64_t)u * rpp;
+            const bool rv = row < r1;
+            hh[u] = make_uint2(0u, 0u); hl[u] = make_uint2(0u, 0u);
+            if (rv) {
+                hh[u] = __ldcs(reinterpret_cast<const uint2*>(H_hi + row * K + k));
+                hl[u] = __ldcs(reinterpret_cast<const uint2*>(H_lo + row * K + k));
             }
 #pragma unroll
-            for (int n = 0; n < N; ++n) d[u][n] = rv ? __ldg(dlogits + (m + u) * N + n) : 0.0f;
+            for (int n = 0; n < N; ++n) d[u][n] = rv ? __ldg(dlogits + row * N + n) : 0.0f;
         }
 #pragma unroll
         for (int u = 0; u < RU; ++u) {
-            const bool rv = m + u < r1;
+            const int64_t row = m + (int64_t)u * rpp;
+            const bool rv = row < r1;
+            const float2 h01 = __half22float2(*reinterpret_cast<const __half2*>(&hh[u].x));
+            const float2 h23 = __half22float2(*reinterpret_cast<const __half2*>(&hh[u].y));
+            const float2 l01 = __half22float2(*reinterpret_cast<const __half2*>(&hl[u].x));
+            const float2 l23 = __half22float2(*reinterpret_cast<const __half2*>(&hl[u].y));
+            // gate on sign(hi): a positive activation below 2^-25 of its tensor's scale rounds to hi = 0 and takes the
+            // other leakyrelu' branch -- the same class of event as a rounding-level flip of a pre-activation at 0
+            const float gate[4] = {h01.x, h01.y, h23.x, h23.y};
+            const float hv[4] = {h01.x + l01.x, h01.y + l01.y, h23.x + l23.x, h23.y + l23.y};   // scaled activation
+            float gv[4];
 #pragma unroll
-            for (int q = 0; q < KPT; ++q) {
-                const int k = 2 * (tid + q * 256);
-                const float2 fh = __half22float2(hh[u][q]), fl = __half22float2(hl[u][q]);
-                const float hv[2] = {fh.x + fl.x, fh.y + fl.y};       // scaled activation
-                const float gate[2] = {fh.x, fh.y};
-                __half oh[2], ol[2];
+            for (int c = 0; c < 4; ++c) {
+                float dx = 0.0f;
 #pragma unroll
-                for (int c = 0; c < 2; ++c) {
-                    float dx = 0.0f;
-#pragma unroll
-                    for (int n = 0; n < N; ++n) {
-                        dx = fmaf(d[u][n], w[q][c][n], dx);
-                        aw[q][c][n] = fmaf(hv[c], d[u][n], aw[q][c][n]);
-                    }
-                    const float g = (gate[c] > 0.0f) ? dx : slope * dx;
-                    if (rv && k + c < K) cs[q][c] += g;
-                    f16_split(g * s_dh, oh[c], ol[c]);
+                for (int n = 0; n < N; ++n) {
+                    dx = fmaf(d[u][n], w[c][n], dx);
+                    aw[c][n] = fmaf(hv[c], d[u][n], aw[c][n]);
                 }
-                if (need_dH && rv && k < K) {
-                    *reinterpret_cast<unsigned int*>(dH_hi + (m + u) * K + k) = pack_h2(oh[0], oh[1]);
-                    *reinterpret_cast<unsigned int*>(dH_lo + (m + u) * K + k) = pack_h2(ol[0], ol[1]);
-                }
+                const float g = (gate[c] > 0.0f) ? dx : slope * dx;
+                cs[c] += g;                                       // d = 0 for rows out of range
+                gv[c] = g * s_dh;
             }
-            if (tid == 0) {
+            if (need_dH && rv) {
+                uint2 oh, ol;
+                f16_split2(gv[0], gv[1], oh.x, ol.x);
+                f16_split2(gv[2], gv[3], oh.y, ol.y);
+                *reinterpret_cast<uint2*>(dH_hi + row * K + k) = oh;
+                *reinterpret_cast<uint2*>(dH_lo + row * K + k) = ol;
+            }
+            if (ct == 0) {
 #pragma unroll
                 for (int n = 0; n < N; ++n) ab[n] += d[u][n];
             }
         }
     }
-    float* pw = partial + (int64_t)blockIdx.x * ((int64_t)K * N + N + K);
+    // fold the row groups (fixed order) and write this CTA's partials
+    const int stride = K * N + N + K;
+    if (active) {
+        float* mine = red + (size_t)rg * stride;
 #pragma unroll
-    for (int q = 0; q < KPT; ++q)
+        for (int c = 0; c < 4; ++c) {
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
-            const int k = 2 * (tid + q * 256) + c;
-            if (k < K) {
-#pragma unroll
-                for (int n = 0; n < N; ++n) pw[k * N + n] = aw[q][c][n] * inv_h;
-                pw[(int64_t)K * N + N + k] = cs[q][c];
-            }
+            for (int n = 0; n < N; ++n) mine[(k + c) * N + n] = aw[c][n] * inv_h;
+            mine[K * N + N + k + c] = cs[c];
         }
-    if (tid == 0) {
+        if (ct == 0) {
 #pragma unroll
-        for (int n = 0; n < N; ++n) pw[(int64_t)K * N + n] = ab[n];
+            for (int n = 0; n < N; ++n) mine[K * N + n] = ab[n];
+        }
+    }
+    __syncthreads();
+    float* pw = partial + (int64_t)blockIdx.x * stride;
+    for (int i = tid; i < stride; i += 256) {
+        float s = 0.0f;
+        for (int g = 0; g < rpp; ++g) s += red[(size_t)g * stride + i];
+        pw[i] = s;
     }
 }
 
@@ -880,14 +954,14 @@ int load_encode16() {
 }
 
 // 2-D map over a row-major [rows][cols] fp16 matrix: box {64 cols, box_rows} with 128B swizzle (operand loads) or
-// {32 cols, box_rows} with 64B swizzle (epilogue stores)
+// {16 cols, box_rows} with 32B swizzle (epilogue stores)
 int make_map16_2d(CUtensorMap* m, const __half* base, int64_t rows, int64_t cols, int box_rows, int box_cols = 64) {
     cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
     cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
     cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = g_encode16(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void*)base, dims, strides, box, estr,
-                            CU_TENSOR_MAP_INTERLEAVE_NONE, box_cols == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, box_cols == 16 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_128B,
                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(f16 2d %lld x %lld) failed: %d", (long long)rows, (long long)cols, (int)r); return PPO_ERR_CUDA; }
     return PPO_OK;
@@ -920,6 +994,7 @@ struct F16State {
     __half* x_hi = nullptr;                  // scaled minibatch features [M][dims[0]] (+ slack)
     __half* x_lo = nullptr;
     std::vector<__half*> act_hi, act_lo;     // act[l], l = 1..L-1
+    std::vector<uint32_t*> act_sign;         // sign bits of act[l] ([M][dims[l]/32]): the leakyrelu' gate of the backward pass
     __half* dz_hi[2] = {nullptr, nullptr};   // ping-pong activation gradients [M][Hmax]
     __half* dz_lo[2] = {nullptr, nullptr};
     float* partial = nullptr;
@@ -983,16 +1058,20 @@ int launch_kk16(ppo_ctx* ctx, const __half* A, const __half* A_lo, const __half*
     PPO_TRY(make_map16_2d(&mAl, A_lo, M, K, F_BM));
     PPO_TRY(make_map16_2d(&mB, B, N, K, BN));
     PPO_TRY(make_map16_2d(&mBl, B_lo, N, K, BN));
-    PPO_TRY(make_map16_2d(&mC, C, M, N, 64, 32));      // store boxes: 64 rows x 32 columns, SWIZZLE_64B
-    PPO_TRY(make_map16_2d(&mCl, C_lo, M, N, 64, 32));
+    PPO_TRY(make_map16_2d(&mC, C, M, N, 32, 16));      // store boxes: 32 rows x 16 columns (one warp's), SWIZZLE_32B
+    PPO_TRY(make_map16_2d(&mCl, C_lo, M, N, 32, 16));
     KK16Params p = base;
+    static const int env_chunk = getenv("PPO_F16_KK_CHUNK") ? atoi(getenv("PPO_F16_KK_CHUNK")) : 0;      // tuning experiments
+    static const float env_comp = getenv("PPO_F16_RZ_COMP") ? (float)atof(getenv("PPO_F16_RZ_COMP")) : -1.0f;
+    p.chunk_kb = env_chunk > 0 ? env_chunk : F_KK_CHUNK_KB;
+    p.rz_comp = env_comp >= 0.0f ? env_comp : F_RZ_COMP;
     p.M = (int)M; p.N = N; p.K = K;
     p.tiles_m = (int)ceil_div(M, F_BM); p.tiles_n = (int)ceil_div(N, BN); p.k_blocks = (int)ceil_div(K, F_BK);
     const int tiles = p.tiles_m * p.tiles_n;
     const int grid = std::min(tiles, ctx->num_sms);
     const size_t smem = KK16Smem<BN>::TOTAL;
     PPO_CUDA(cudaFuncSetAttribute(f16_gemm_kk_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    f16_gemm_kk_kernel<BN><<<grid, F_THREADS, smem, ctx->stream>>>(mA, mAl, mB, mBl, mC, mCl, p);
+    f16_gemm_kk_kernel<BN><<<grid, F_KK_THREADS, smem, ctx->stream>>>(mA, mAl, mB, mBl, mC, mCl, p);
     ctx->launches += 1;
     PPO_CUDA(cudaGetLastError());
     return PPO_OK;
@@ -1002,7 +1081,12 @@ int kk16_dispatch(ppo_ctx* ctx, const __half* A, const __half* A_lo, const __hal
                   int64_t M, int N, int K, const KK16Params& base) {
     PPO_REQUIRE(M < ((int64_t)1 << 31), "f16 gemm: M too large");
     PPO_REQUIRE(K % 8 == 0 && N % 32 == 0, "f16 gemm: K %% 8 and N %% 32 required (K=%d N=%d)", K, N);
-    if (N > 128) return launch_kk16<256>(ctx, A, A_lo, B, B_lo, C, C_lo, M, N, K, base);
+    // tile width: 128 x 256 tiles need the fewest operand bytes per MMA (the kernel is L2-feed bound at K = 512); for a
+    // short contraction (K <= 128: the first layer) the epilogue dominates and 128 x 128 tiles with 4 TMEM stages keep
+    // it off the critical path (measured 0.56 vs 0.66 ms at M = 2^20, K = 64, N = 512)
+    static const int force128 = getenv("PPO_F16_BN128") ? atoi(getenv("PPO_F16_BN128")) : -1;   // tuning experiments
+    const bool wide = force128 >= 0 ? !force128 : (K > 128);
+    if (N > 128 && wide) return launch_kk16<256>(ctx, A, A_lo, B, B_lo, C, C_lo, M, N, K, base);
     return launch_kk16<128>(ctx, A, A_lo, B, B_lo, C, C_lo, M, N, K, base);
 }
 
@@ -1077,20 +1161,20 @@ int head_fwd16(ppo_ctx* ctx, const __half* H_hi, const __half* H_lo, const float
 int head_bwd16(ppo_ctx* ctx, const __half* H_hi, const __half* H_lo, const float* dlogits, const float* W, __half* dH_hi,
                __half* dH_lo, float* dW, float* db, float* db_below, int64_t M, int K, int N, float slope, float* partial,
                size_t partial_bytes, const float* sc_h, const float* sc_dh) {
-    PPO_REQUIRE(N >= 1 && N <= 4 && K % 2 == 0 && K <= 1024, "f16 head_bwd: needs N <= 4 and even K <= 1024 (K=%d N=%d)", K, N);
+    PPO_REQUIRE(N >= 1 && N <= 4 && K % 4 == 0 && K >= 4 && K <= 1024, "f16 head_bwd: needs N <= 4, K %% 4 == 0, K <= 1024 (K=%d N=%d)", K, N);
     const int64_t ctas = head16_ctas(M, ctx->num_sms);
     const int64_t rows = ceil_div(M, ctas);
     const int64_t stride = (int64_t)K * N + N + K;
     PPO_REQUIRE((size_t)ctas * stride * sizeof(float) <= partial_bytes, "f16 head_bwd: partial buffer too small");
-    const int kpt = (int)ceil_div(K, 512);
     const int need_dH = dH_hi != nullptr ? 1 : 0;
-#define PPO_HEAD_BWD16(N_, Q_)                                                                                       \
-    if (N == N_ && kpt == Q_)                                                                                        \
-        head_bwd16_kernel<N_, Q_><<<(unsigned)ctas, 256, 0, ctx->stream>>>(H_hi, H_lo, dlogits, W, dH_hi, dH_lo, partial, M, \
-                                                                           K, slope, rows, need_dH, sc_h, sc_dh);
-    PPO_HEAD_BWD16(1, 1) PPO_HEAD_BWD16(1, 2) PPO_HEAD_BWD16(2, 1) PPO_HEAD_BWD16(2, 2)
-    PPO_HEAD_BWD16(3, 1) PPO_HEAD_BWD16(3, 2) PPO_HEAD_BWD16(4, 1) PPO_HEAD_BWD16(4, 2)
-#undef PPO_HEAD_BWD16
+    const int rpp = 256 / (K / 4);
+    const size_t smem = (size_t)rpp * stride * sizeof(float);
+    switch (N) {
+        case 1: head_bwd16_kernel<1><<<(unsigned)ctas, 256, smem, ctx->stream>>>(H_hi, H_lo, dlogits, W, dH_hi, dH_lo, partial, M, K, slope, rows, need_dH, sc_h, sc_dh); break;
+        case 2: head_bwd16_kernel<2><<<(unsigned)ctas, 256, smem, ctx->stream>>>(H_hi, H_lo, dlogits, W, dH_hi, dH_lo, partial, M, K, slope, rows, need_dH, sc_h, sc_dh); break;
+        case 3: head_bwd16_kernel<3><<<(unsigned)ctas, 256, smem, ctx->stream>>>(H_hi, H_lo, dlogits, W, dH_hi, dH_lo, partial, M, K, slope, rows, need_dH, sc_h, sc_dh); break;
+        default: head_bwd16_kernel<4><<<(unsigned)ctas, 256, smem, ctx->stream>>>(H_hi, H_lo, dlogits, W, dH_hi, dH_lo, partial, M, K, slope, rows, need_dH, sc_h, sc_dh); break;
+    }
     ctx->launches += 1;
     PPO_CUDA(cudaGetLastError());
     const int64_t cnt = (int64_t)K * N;
@@ -1113,11 +1197,13 @@ int ensure_f16_workspace(ppo_policy* p, int64_t tokens) {
     fr(st->x_hi); fr(st->x_lo); fr(st->dz_hi[0]); fr(st->dz_hi[1]); fr(st->dz_lo[0]); fr(st->dz_lo[1]); fr(st->partial);
     for (auto& a : st->act_hi) fr(a);
     for (auto& a : st->act_lo) fr(a);
+    for (auto& a : st->act_sign) fr(a);
     const int L = p->L;
     int hmax = 1;
     for (int l = 1; l < L; ++l) hmax = std::max(hmax, p->dims[l]);
     st->act_hi.assign(L + 1, nullptr);
     st->act_lo.assign(L + 1, nullptr);
+    st->act_sign.assign(L + 1, nullptr);
     // +256 B of slack: the MN-major 3-D view reads whole 64-column blocks of the last row
     const size_t slack = 256;
     PPO_CUDA(cudaMalloc((void**)&st->x_hi, (size_t)tokens * p->dims[0] * 2 + slack));
@@ -1125,6 +1211,7 @@ int ensure_f16_workspace(ppo_policy* p, int64_t tokens) {
     for (int l = 1; l < L; ++l) {
         PPO_CUDA(cudaMalloc((void**)&st->act_hi[l], (size_t)tokens * p->dims[l] * 2 + slack));
         PPO_CUDA(cudaMalloc((void**)&st->act_lo[l], (size_t)tokens * p->dims[l] * 2 + slack));
+        if (l < L - 1) PPO_CUDA(cudaMalloc((void**)&st->act_sign[l], sign_words(tokens, p->dims[l]) * 4));   // (the head gates on sign(hi))
     }
     for (int i = 0; i < 2; ++i) {
         PPO_CUDA(cudaMalloc((void**)&st->dz_hi[i], (size_t)tokens * hmax * 2 + slack));
@@ -1225,6 +1312,7 @@ int f16_forward(ppo_policy* p, const float* X, int64_t M) {
         kp.sc_a = st->sc + 2 * sc_act(l); kp.sc_b = st->sc + 2 * sc_w(L, l); kp.sc_c = st->sc + 2 * sc_act(l + 1);
         const __half* A_hi = (l == 0) ? st->x_hi : st->act_hi[l];
         const __half* A_lo = (l == 0) ? st->x_lo : st->act_lo[l];
+        kp.signs_out = st->act_sign[l + 1];      // nullptr for the last hidden layer
         PPO_TRY(kk16_dispatch(ctx, A_hi, A_lo, ly.WT_hi, ly.WT_lo, st->act_hi[l + 1], st->act_lo[l + 1], M, N, K, kp));
     }
     return head_fwd16(ctx, st->act_hi[L - 1], st->act_lo[L - 1], p->params + p->w_off[L - 1], p->params + p->b_off[L - 1],
@@ -1256,7 +1344,7 @@ int f16_backward(ppo_policy* p, int64_t M) {
                         K, N, st->sc + 2 * sc_act(l), sc_dy));
         if (l > 0) {
             KK16Params kp{};
-            kp.epi = F_EPI_DGRAD; kp.act = 0; kp.slope = p->slope; kp.gate = X_hi;
+            kp.epi = F_EPI_DGRAD; kp.act = 0; kp.slope = p->slope; kp.gate = st->act_sign[l];
             kp.colsum_partial = st->partial;
             kp.sc_a = sc_dy; kp.sc_b = st->sc + 2 * sc_w(L, l); kp.sc_c = st->sc + 2 * sc_dz(L, l - 1);
             // dX[M, K] = dY[M, N] * W[K, N]^T : A = dY (K-major in N), B = W rows (K-major in N)
@@ -1276,6 +1364,7 @@ void f16_destroy(ppo_policy* p) {
     fr(st->x_hi); fr(st->x_lo); fr(st->dz_hi[0]); fr(st->dz_hi[1]); fr(st->dz_lo[0]); fr(st->dz_lo[1]); fr(st->partial);
     for (auto& a : st->act_hi) fr(a);
     for (auto& a : st->act_lo) fr(a);
+    for (auto& a : st->act_sign) fr(a);
     fr(st->sc); fr(st->st);
     delete st;
     p->f16 = nullptr;
@@ -1307,20 +1396,20 @@ int f16_test_set_scale(ppo_ctx* ctx, float* sc, float bound) {
     return PPO_OK;
 }
 int f16_test_fwd(ppo_ctx* ctx, const __half* X_hi, const __half* X_lo, const __half* WT_hi, const __half* WT_lo,
-                 const float* bias, __half* Y_hi, __half* Y_lo, int64_t M, int K, int N, int act, float slope,
+                 const float* bias, __half* Y_hi, __half* Y_lo, uint32_t* Y_sign, int64_t M, int K, int N, int act, float slope,
                  const float* sc_x, const float* sc_w, const float* sc_y) {
     PPO_TRY(load_encode16());
     KK16Params kp{};
-    kp.epi = F_EPI_FWD; kp.act = act; kp.slope = slope; kp.bias = bias;
+    kp.epi = F_EPI_FWD; kp.act = act; kp.slope = slope; kp.bias = bias; kp.signs_out = Y_sign;
     kp.sc_a = sc_x; kp.sc_b = sc_w; kp.sc_c = sc_y;
     return kk16_dispatch(ctx, X_hi, X_lo, WT_hi, WT_lo, Y_hi, Y_lo, M, N, K, kp);
 }
 int f16_test_dgrad(ppo_ctx* ctx, const __half* dY_hi, const __half* dY_lo, const __half* W_hi, const __half* W_lo,
-                   const __half* gate_hi, __half* dX_hi, __half* dX_lo, int64_t M, int K, int N, float slope,
+                   const uint32_t* gate, __half* dX_hi, __half* dX_lo, int64_t M, int K, int N, float slope,
                    float* colsum_scratch, float* colsum_out, const float* sc_dy, const float* sc_w, const float* sc_dx) {
     PPO_TRY(load_encode16());
     KK16Params kp{};
-    kp.epi = F_EPI_DGRAD; kp.slope = slope; kp.gate = gate_hi;
+    kp.epi = F_EPI_DGRAD; kp.slope = slope; kp.gate = gate;
     kp.colsum_partial = colsum_out ? colsum_scratch : nullptr;
     kp.sc_a = sc_dy; kp.sc_b = sc_w; kp.sc_c = sc_dx;
     PPO_TRY(kk16_dispatch(ctx, dY_hi, dY_lo, W_hi, W_lo, dX_hi, dX_lo, M, K, N, kp));
@@ -1341,6 +1430,14 @@ int f16_test_join(ppo_ctx* ctx, const __half* hi, const __half* lo, int64_t n, c
     PPO_CUDA(cudaGetLastError());
     return PPO_OK;
 }
+int f16_test_signbits(ppo_ctx* ctx, const float* x, int64_t M, int N, uint32_t* out) {
+    PPO_REQUIRE(N % 32 == 0, "signbits: N %% 32");
+    signbits_kernel<<<(unsigned)std::min<int64_t>(ceil_div(M * (N / 32), 256), (int64_t)ctx->num_sms * 16), 256, 0, ctx->stream>>>(x, M, N, out);
+    ctx->launches += 1;
+    PPO_CUDA(cudaGetLastError());
+    return PPO_OK;
+}
+size_t f16_test_sign_words(int64_t M, int N) { return sign_words(M, N); }
 size_t f16_test_partial_bytes(ppo_ctx* ctx, int64_t M, int K, int N) { return f16_partial_bytes(M, K, N, ctx->num_sms); }
 int f16_test_head_fwd(ppo_ctx* ctx, const __half* H_hi, const __half* H_lo, const float* W, const float* bias, float* logits,
                       int64_t M, int K, int N, const float* sc_h) {

@@ -23,14 +23,16 @@ int f16_test_weight(ppo_ctx* ctx, const float* W, __half* W_hi, __half* W_lo, __
                     float* sc, unsigned* st);
 int f16_test_set_scale(ppo_ctx* ctx, float* sc, float bound);
 int f16_test_fwd(ppo_ctx* ctx, const __half* X_hi, const __half* X_lo, const __half* WT_hi, const __half* WT_lo,
-                 const float* bias, __half* Y_hi, __half* Y_lo, int64_t M, int K, int N, int act, float slope,
+                 const float* bias, __half* Y_hi, __half* Y_lo, uint32_t* Y_sign, int64_t M, int K, int N, int act, float slope,
                  const float* sc_x, const float* sc_w, const float* sc_y);
 int f16_test_dgrad(ppo_ctx* ctx, const __half* dY_hi, const __half* dY_lo, const __half* W_hi, const __half* W_lo,
-                   const __half* gate_hi, __half* dX_hi, __half* dX_lo, int64_t M, int K, int N, float slope,
+                   const uint32_t* gate, __half* dX_hi, __half* dX_lo, int64_t M, int K, int N, float slope,
                    float* colsum_scratch, float* colsum_out, const float* sc_dy, const float* sc_w, const float* sc_dx);
 int f16_test_wgrad(ppo_ctx* ctx, const __half* X_hi, const __half* X_lo, const __half* dY_hi, const __half* dY_lo, float* dW,
                    float* partial, size_t partial_bytes, int64_t M, int K, int N, const float* sc_x, const float* sc_dy);
 int f16_test_join(ppo_ctx* ctx, const __half* hi, const __half* lo, int64_t n, const float* sc, float* out);
+int f16_test_signbits(ppo_ctx* ctx, const float* x, int64_t M, int N, uint32_t* out);   // N % 32 == 0; out: f16_test_sign_words(M, N)
+size_t f16_test_sign_words(int64_t M, int N);
 size_t f16_test_partial_bytes(ppo_ctx* ctx, int64_t M, int K, int N);
 int f16_test_head_fwd(ppo_ctx* ctx, const __half* H_hi, const __half* H_lo, const float* W, const float* bias, float* logits,
                       int64_t M, int K, int N, const float* sc_h);
