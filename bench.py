@@ -309,6 +309,7 @@ def _run_ours(args):
 
         hbm("K1_scan_namedN", "scan", cfg.N, 15)
         hbm("K1_scan_64M", "scan", 64 * 1024 * 1024, 15, iters=5)
+        hbm("K1K2_scan_64M_with_norm_stats", "scan_norm", 64 * 1024 * 1024, 15, iters=5)
         hbm("K3_shuffle", "shuffle", cfg.N)
         hbm("K4_gather_ldg", "gather0", cfg.N, cfg.nf * cfg.nhe, cfg.A, B_local)
         hbm("K4_gather_bulk", "gather1", cfg.N, cfg.nf * cfg.nhe, cfg.A, B_local)

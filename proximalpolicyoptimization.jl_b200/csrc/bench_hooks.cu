@@ -114,7 +114,7 @@ extern "C" int ppo_bench_kernel(ppo_ctx* ctx, const char* which, int64_t n, int 
     PPO_REQUIRE(n >= 1 && iters >= 1, "bench_kernel: n=%lld iters=%d", (long long)n, iters);
     Scope sc;
     const std::string w(which);
-    if (w == "scan") {
+    if (w == "scan" || w == "scan_norm") {      // scan_norm: with the K2 statistics of the normalisation extension fused in
         float *r, *o; uint8_t* t; double* stats;
         const int64_t n16 = round_up(n, SCAN_TILE);
         PPO_TRY(sc.alloc(&r, (size_t)n16)); PPO_TRY(sc.alloc(&o, (size_t)n16)); PPO_TRY(sc.alloc(&t, (size_t)n16));
@@ -125,7 +125,7 @@ extern "C" int ppo_bench_kernel(ppo_ctx* ctx, const char* which, int64_t n, int 
         const double disc = (b == 0) ? 1.0 : 0.99;
         g_scan_dbg = c;   // timing experiments only (1: skip look-back, 4: skip stats, 8: no look-ahead)
         int st = time_loop(ctx, sc, iters, flush_l2_flag,
-                           [&]() { return launch_returns_scan(ctx, r, o, t, n, disc, 0, stats, scratch); }, ms_out);
+                           [&]() { return launch_returns_scan(ctx, r, o, t, n, disc, 0, w == "scan_norm" ? stats : nullptr, scratch); }, ms_out);
         g_scan_dbg = 0;
         PPO_TRY(st);
         *work_out = 9.0 * (double)n;

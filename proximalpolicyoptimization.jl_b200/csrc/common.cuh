@@ -96,6 +96,7 @@ struct ppo_buf {
     double* d_tile_stats = nullptr; // per scan tile {sum, sumsq}
     int64_t n_tiles_stats = 0;
     bool stats_valid = false;
+    bool returns_valid = false;     // reward[] holds returns (compute_returns ran since the last append)
     ppo_batch batch;             // gather destination
 };
 
@@ -150,6 +151,9 @@ constexpr int SCAN_STATS_PER_TILE = SCAN_THREADS / 32;   // one {sum, sumsq} pai
 size_t scan_scratch_bytes(int64_t n);
 int launch_returns_scan(ppo_ctx* ctx, const float* reward_in, float* returns_out, const uint8_t* terminal,
                         int64_t n, double discount, int discount_is_f32, double* tile_stats, void* scratch);
+// tile_stats == nullptr in launch_returns_scan skips the K2 statistics (advantage normalisation is an extension, off by
+// default); launch_returns_stats produces the identical partials from the finished returns
+int launch_returns_stats(ppo_ctx* ctx, const float* returns, int64_t n, double* tile_stats);
 int launch_norm_finalize(ppo_ctx* ctx, const double* tile_stats, int64_t n_tiles, int64_t n,
                          double eps, float* d_norm);
 

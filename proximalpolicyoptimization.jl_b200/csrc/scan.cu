@@ -97,7 +97,9 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 // Persistent CTAs: block b scans tiles b, b + G, b + 2G, ... (tile ids count from the RIGHT end, the direction of the
 // scan), G = all co-resident CTAs.  While tile i is being scanned, the cp.async copies of tile i+1 are in flight, so
 // HBM always has work queued; before this software pipeline the kernel was latency bound at ~55 % of the roofline.
-template <bool F32CARRY>
+// G1: discount == 1 (every in-tree use of the reference): g * v == v exactly, so the multiplies are dropped
+// (bit-identical results, fewer Float64 instructions).
+template <bool F32CARRY, bool G1>
 __global__ void __launch_bounds__(SCAN_THREADS, 4)
 returns_scan_kernel(const float* __restrict__ rew, float* __restrict__ out, const uint8_t* __restrict__ term, int64_t n,
                     double g, double g8, int tiles, ScanScratch sc, double* __restrict__ tile_stats, int dbg) {
@@ -176,8 +178,12 @@ returns_scan_kernel(const float* __restrict__ rew, float* __restrict__ out, cons
                 tm[i >> 2] |= tb << (8 * (i & 3));
             }
         }
-        auto is_term = [&](int i) -> bool { return ((tm[i >> 2] >> (8 * (i & 3))) & 0xffu) != 0; };
+        // one bit per item (terminal bytes are 0/1: the append path normalises them)
+        const uint32_t tbits = ((tm[0] * 0x01020408u) >> 24 & 0xfu) | (((tm[1] * 0x01020408u) >> 24 & 0xfu) << 4) |
+                               (((tm[2] * 0x01020408u) >> 24 & 0xfu) << 8) | (((tm[3] * 0x01020408u) >> 24 & 0xfu) << 12);
+        auto is_term = [&](int i) -> bool { return (tbits >> i) & 1u; };
 
+        if (!(dbg & 16)) {
         // 0. look-ahead (warp 0): the 128 transitions right of the tile, composed into one map.  With episodic
         //    data an episode end almost always lies inside it (A == 0), so the tile's incoming carry is known
         //    without waiting for any other CTA; only tiles inside very long episodes use the look-back below.
@@ -199,6 +205,22 @@ returns_scan_kernel(const float* __restrict__ rew, float* __restrict__ out, cons
                     lt[j] = in ? (term[e0 + j] != 0) : true;
                 }
             }
+            if (G1) {
+                // discount 1: the carry is the plain sum of the rewards up to and including the first episode end in the
+                // window (Float64 sums of <= 128 Float32 rewards are exact unless their exponents span > 29 bits, so the
+                // order of the additions does not matter); found with one ballot instead of a scan of affine maps
+                const int firstj = lt[0] ? 0 : (lt[1] ? 1 : (lt[2] ? 2 : (lt[3] ? 3 : 4)));
+                const unsigned has = __ballot_sync(0xffffffffu, firstj < 4);
+                const int fl = has ? (__ffs(has) - 1) : 32;
+                const int upto = lane < fl ? 3 : (lane == fl ? firstj : -1);
+                double part = 0.0;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) part += (j <= upto) ? (double)lr[j] : 0.0;
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) part += __shfl_xor_sync(0xffffffffu, part, d);
+                lk.A = has ? 0.0 : 1.0;
+                lk.B = part;
+            } else {
 #pragma unroll
             for (int j = 3; j >= 0; --j) {
                 const double a = lt[j] ? 0.0 : g;
@@ -212,6 +234,7 @@ returns_scan_kernel(const float* __restrict__ rew, float* __restrict__ out, cons
                 o.B = __shfl_down_sync(0xffffffffu, lk.B, d);
                 if (lane + d < 32) lk = compose(lk, o);
             }
+            }
             if (lane == 0) { s_lookA = lk.A; s_lookB = lk.B; }
         }
 
@@ -224,10 +247,15 @@ returns_scan_kernel(const float* __restrict__ rew, float* __restrict__ out, cons
 #pragma unroll
         for (int i = HALF - 1; i >= 0; --i) {
             const bool t_hi = is_term(i + HALF), t_lo = is_term(i);
-            th |= t_hi; tl |= t_lo;
-            Bh = __dadd_rn((double)r[i + HALF], __dmul_rn(t_hi ? 0.0 : g, Bh));
-            Bl = __dadd_rn((double)r[i], __dmul_rn(t_lo ? 0.0 : g, Bl));
+            if (G1) {
+                Bh = __dadd_rn((double)r[i + HALF], t_hi ? 0.0 : Bh);
+                Bl = __dadd_rn((double)r[i], t_lo ? 0.0 : Bl);
+            } else {
+                Bh = __dadd_rn((double)r[i + HALF], __dmul_rn(t_hi ? 0.0 : g, Bh));
+                Bl = __dadd_rn((double)r[i], __dmul_rn(t_lo ? 0.0 : g, Bl));
+            }
         }
+        th = (tbits >> HALF) != 0u; tl = (tbits & ((1u << HALF) - 1u)) != 0u;
         const double Ah = th ? 0.0 : g8, Al = tl ? 0.0 : g8;
         Map me;
         me.A = Al * Ah;
@@ -317,12 +345,13 @@ returns_scan_kernel(const float* __restrict__ rew, float* __restrict__ out, cons
             for (int i = HALF - 1; i >= 0; --i) {
                 if (is_term(i + HALF)) vh = 0.0;
                 if (is_term(i)) vl = 0.0;
-                vh = __dadd_rn((double)r[i + HALF], __dmul_rn(g, vh));
-                vl = __dadd_rn((double)r[i], __dmul_rn(g, vl));
+                vh = __dadd_rn((double)r[i + HALF], G1 ? vh : __dmul_rn(g, vh));
+                vl = __dadd_rn((double)r[i], G1 ? vl : __dmul_rn(g, vl));
                 r[i + HALF] = (float)vh;
                 r[i] = (float)vl;
             }
         }
+        }   // dbg & 16
         float lsum = 0.0f, lsq = 0.0f;
         if (full_tile) {
             // back through the (now free) stage for coalesced 128-bit stores
@@ -344,20 +373,41 @@ returns_scan_kernel(const float* __restrict__ rew, float* __restrict__ out, cons
             }
         }
 
-        // 6. K2 statistics of the returns: one {sum, sumsq} pair per warp (fp32 partials over 16 values per
-        //    thread, Float64 from there on, folded in a fixed order by norm_finalize_kernel => deterministic)
-        if (!(dbg & 4)) {
-            double dsum = (double)lsum, dsq = (double)lsq;
+        // 6. K2 statistics of the returns: one {sum, sumsq} pair per warp (fp32 partials over the warp's 512 values,
+        //    Float64 from there on, folded in a fixed order by norm_finalize_kernel => deterministic)
+        if (tile_stats != nullptr && !(dbg & 4)) {
 #pragma unroll
             for (int d = 16; d > 0; d >>= 1) {
-                dsum += __shfl_down_sync(0xffffffffu, dsum, d);
-                dsq += __shfl_down_sync(0xffffffffu, dsq, d);
+                lsum += __shfl_down_sync(0xffffffffu, lsum, d);
+                lsq += __shfl_down_sync(0xffffffffu, lsq, d);
             }
             if (lane == 0) {
-                tile_stats[2 * ((int64_t)tile_idx * NW + warp)] = dsum;
-                tile_stats[2 * ((int64_t)tile_idx * NW + warp) + 1] = dsq;
+                tile_stats[2 * ((int64_t)tile_idx * NW + warp)] = (double)lsum;
+                tile_stats[2 * ((int64_t)tile_idx * NW + warp) + 1] = (double)lsq;
             }
         }
+    }
+}
+
+// K2 statistics as a stand-alone pass over the returns (used when advantage normalisation is switched on after
+// compute_returns ran without it): the same partition and the same order of additions as step 6 of the scan kernel.
+__global__ void __launch_bounds__(SCAN_THREADS)
+returns_stats_kernel(const float* __restrict__ ret, int64_t n, double* __restrict__ tile_stats) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t tile_idx = blockIdx.x;
+    const int64_t base = tile_idx * SCAN_TILE + (int64_t)tid * SCAN_ITEMS;
+    float lsum = 0.0f, lsq = 0.0f;
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; ++i)
+        if (base + i < n) { const float v = ret[base + i]; lsum += v; lsq = fmaf(v, v, lsq); }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        lsum += __shfl_down_sync(0xffffffffu, lsum, d);
+        lsq += __shfl_down_sync(0xffffffffu, lsq, d);
+    }
+    if (lane == 0) {
+        tile_stats[2 * (tile_idx * (SCAN_THREADS / 32) + warp)] = (double)lsum;
+        tile_stats[2 * (tile_idx * (SCAN_THREADS / 32) + warp) + 1] = (double)lsq;
     }
 }
 
@@ -405,21 +455,26 @@ int launch_returns_scan(ppo_ctx* ctx, const float* reward_in, float* returns_out
     // persistent grid: every CTA must be co-resident (the look-back waits on lower tile ids)
     const size_t smem = 2 * sizeof(ScanStage);
     int occ = 0;
-    if (discount_is_f32) {
-        PPO_CUDA(cudaFuncSetAttribute(returns_scan_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        PPO_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, returns_scan_kernel<true>, SCAN_THREADS, smem));
-    } else {
-        PPO_CUDA(cudaFuncSetAttribute(returns_scan_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        PPO_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, returns_scan_kernel<false>, SCAN_THREADS, smem));
-    }
-    PPO_REQUIRE(occ >= 1, "returns scan: kernel does not fit on an SM");
-    const int64_t grid = std::min<int64_t>(tiles, (int64_t)ctx->num_sms * occ);
-    if (discount_is_f32)
-        returns_scan_kernel<true><<<(unsigned)grid, SCAN_THREADS, smem, ctx->stream>>>(
-            reward_in, returns_out, terminal, n, g, g8, (int)tiles, sc, tile_stats, g_scan_dbg);
-    else
-        returns_scan_kernel<false><<<(unsigned)grid, SCAN_THREADS, smem, ctx->stream>>>(
-            reward_in, returns_out, terminal, n, g, g8, (int)tiles, sc, tile_stats, g_scan_dbg);
+    const bool g1 = (g == 1.0);
+    auto launch = [&](auto kern) -> int {
+        PPO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        PPO_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, SCAN_THREADS, smem));
+        PPO_REQUIRE(occ >= 1, "returns scan: kernel does not fit on an SM");
+        const int64_t grid = std::min<int64_t>(tiles, (int64_t)ctx->num_sms * occ);
+        kern<<<(unsigned)grid, SCAN_THREADS, smem, ctx->stream>>>(reward_in, returns_out, terminal, n, g, g8, (int)tiles, sc,
+                                                                  tile_stats, g_scan_dbg);
+        return PPO_OK;
+    };
+    if (discount_is_f32) PPO_TRY(g1 ? launch(returns_scan_kernel<true, true>) : launch(returns_scan_kernel<true, false>));
+    else PPO_TRY(g1 ? launch(returns_scan_kernel<false, true>) : launch(returns_scan_kernel<false, false>));
+    ctx->launches += 1;
+    PPO_CUDA(cudaGetLastError());
+    return PPO_OK;
+}
+
+int launch_returns_stats(ppo_ctx* ctx, const float* returns, int64_t n, double* tile_stats) {
+    if (n <= 0) return PPO_OK;
+    returns_stats_kernel<<<(unsigned)ceil_div(n, SCAN_TILE), SCAN_THREADS, 0, ctx->stream>>>(returns, n, tile_stats);
     ctx->launches += 1;
     PPO_CUDA(cudaGetLastError());
     return PPO_OK;

@@ -11,6 +11,7 @@ def hbm(name, which, n, a=0, b=0, c=0, iters=10):
 hbm("scan 1M", "scan", 1 << 20, 15)
 hbm("scan 64M", "scan", 64 << 20, 15, iters=5)
 hbm("scan 64M gamma.99", "scan", 64 << 20, 15, 1, iters=5)
+hbm("scan 64M +K2 stats", "scan_norm", 64 << 20, 15, iters=5)
 hbm("scan 64M no-terminals", "scan", 64 << 20, 1 << 30, 1, iters=5)
 hbm("loss 64k A=64", "loss", 65536, 64)
 hbm("loss 1M A=64", "loss", 1 << 20, 64, iters=5)
