@@ -341,13 +341,16 @@ def _run_ours(args):
         kname = {"tf32x3": "tc_gemm_kk_kernel<256>", "f16x3": "f16_gemm_kk_kernel<256>", "fp32": "sgemm_kernel"}[args.gemm]
         roofline = {"bound": "tensor", "achieved": ach, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
                     "frac": round(ach / pk["bf16_sustained"], 4),
-                    "traffic": 8.65e9 if (args.gemm == "tf32x3" and M == 1 << 20 and cfg.H == 512) else None,
+                    "traffic": ({"tf32x3": 8.65e9, "f16x3": 4.34e9}.get(args.gemm)
+                                if (M == 1 << 20 and cfg.H == 512) else None),
                     "kernel": kname + f" (hidden Dense forward, M={M}, K=N={cfg.H})",
                     "ms_per_launch": fwd["ms"],
                     "peak_source": pk["src"] + " bf16 sustained (MEASURED_PEAKS.json; kernel timed inside a long step)",
                     "tensor_flops_issued_tflops": round(ach * passes, 2),
                     "frac_of_3pass_ceiling": round(ach / ceiling, 4) if passes == 3 else None,
-                    "traffic_source": "ncu --set full, profiles/r01_ncu_summary.md (dram read 4.38 GB + write 4.27 GB per launch)",
+                    "traffic_source": {"tf32x3": "ncu --set full, profiles/r01_ncu_summary.md (dram read 4.38 GB + write 4.27 GB per launch)",
+                                       "f16x3": "ncu --set full, profiles/r01_f16_ncu.md (dram read 2.17 GB + write 2.18 GB per launch "
+                                                "= the algorithmic bytes of the fp16 hi/lo pairs)"}.get(args.gemm),
                     "detail": dom}
         # the CPU baseline is timed at N = 1 only (torchrun pins OMP_NUM_THREADS=1 and the ranks share the host)
         cpu = cpu_baseline(cfg, data, W, b) if world == 1 else None
@@ -361,7 +364,7 @@ def _run_ours(args):
                        "global_minibatch": B_local * world, "mlp": f"{cfg.L}x{cfg.H}", "nf": cfg.nf, "nhe": cfg.nhe,
                        "actions_per_state": cfg.A, "epochs_per_step": 1, "gemm_engine": args.gemm,
                        "parallelism": f"dp{world}" if world > 1 else "single",
-                       "l2": "step inputs (4.6 GB) exceed L2; per-kernel timings flush L2 between launches"},
+                       "l2": "step inputs (4.6 GB) exceed L2; per-kernel timings flush L2 between launches (write 256 MB, then read 256 MB so that no dirty flush lines are written back inside the timed kernel)"},
             "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu, "e2e": e2e,
             "gpu_launches": launches, "clocks": clocks,
             "loss_last_step": [float(last["loss"][0][0]), float(last["loss"][1][0])],
