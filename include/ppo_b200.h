@@ -159,6 +159,15 @@ int64_t ppo_policy_num_params(ppo_policy* p);
  * probs[nb][A] = softmax(reshape(policy(feat), :, nb) + mask). */
 int ppo_batch_action_probabilities(ppo_policy* p, int64_t nb, int nhe, const float* feat,
                                    const float* mask, float* probs_out);
+/* Batched rollout inference.  The reference samples one state at a time on the host
+   (src/collect_rollouts.jl:1-15: action_probabilities -> rand(Categorical(ap))); this entry does nb states in one call:
+   policy forward + masked softmax + one inverse-CDF categorical draw per state.  Draw i uses output i of the
+   splitmix64 stream of `seed` (top 24 bits as a Float32 uniform), the cumulative sum is sequential Float32 as in
+   Distributions.jl.  action1_out: 1-based Int64 [nb]; prob_out: probability of the drawn action [nb] (what update!
+   stores as selected_action_probability); probs_out (optional, may be NULL): all probabilities [nb][A]. */
+int ppo_sample_actions(ppo_policy* p, int64_t nb, int nhe, const float* feat, const float* mask, uint64_t seed,
+                       int64_t* action1_out, float* prob_out, float* probs_out);
+
 
 /* ---- optimiser: Flux.Optimise.Adam, call site src/train.jl:81 ----------------------------- */
 int ppo_adam_create(ppo_policy* p, double eta, double beta1, double beta2, double eps, ppo_opt** out);

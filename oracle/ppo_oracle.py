@@ -539,3 +539,43 @@ def normalize_advantage(returns, eps=1e-8):
     mu = r.mean()
     sd = np.sqrt(np.maximum((r * r).mean() - mu * mu, 0.0))
     return ((r - mu) / (sd + eps)).astype(F32)
+
+
+# ---------------------------------------------------------------------------------------------
+# batched rollout inference (extension; the reference samples one state at a time on the host)
+# ---------------------------------------------------------------------------------------------
+def sample_uniforms(seed, n):
+    """Float32 uniforms of ppo_sample_actions: draw i = top 24 bits of output i of the splitmix64 stream of `seed`."""
+    s = int(seed) & _M64
+    out = np.empty(n, np.float32)
+    for i in range(n):
+        s, z = _splitmix64(s)
+        out[i] = np.float32(z >> 40) * np.float32(1.0 / 16777216.0)
+    return out
+
+
+def sample_actions_from_probs(probs, seed):
+    """src/collect_rollouts.jl:5-7 ``rand(Categorical(ap))`` for every row of probs [nb, A] (Float32).
+
+    ASSUMPTION (Distributions.jl is un-vendored and un-pinned): inverse CDF with a sequential cumulative sum in the
+    element type of the probabilities, ``while cp <= draw && i < n``.  The RNG stream cannot be Julia's; the draws
+    are sample_uniforms(seed, nb).  Extension: if rounding leaves the total below the draw, the last action with
+    non-zero probability is returned (never a masked one).  Returns 1-based actions and their probabilities."""
+    probs = np.asarray(probs, np.float32)
+    nb, A = probs.shape
+    u = sample_uniforms(seed, nb)
+    act = np.empty(nb, np.int64)
+    for b in range(nb):
+        p = probs[b]
+        c = np.float32(p[0])
+        a = 0
+        last = 0 if p[0] > 0 else -1
+        while c <= u[b] and a < A - 1:
+            a += 1
+            c = np.float32(c + p[a])
+            if p[a] > 0:
+                last = a
+        if not p[a] > 0 and last >= 0:
+            a = last
+        act[b] = a + 1
+    return act, probs[np.arange(nb), act - 1]

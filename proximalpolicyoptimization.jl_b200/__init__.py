@@ -10,7 +10,7 @@ from .rollout_buffer import (DeviceRollouts, DeviceDataset, StateData, batch_sta
                              compute_state_value_, permute_, shuffle_, construct_dataset, get_sample, get_batch)
 from .collect_rollouts import (collect_step_data_, collect_episode_data_, collect_rollouts_, compute_returns)
 from .policy import Policy, Adam, Optimiser, action_probabilities, batch_action_probabilities, \
-    number_of_actions_per_state
+    number_of_actions_per_state, batch_sample_actions
 from .train import (simplified_ppo_clip, get_linear_action_index, batch_advantage, step_batch_, step_epoch_,
                     ppo_train_, ppo_iterate_, get_optimizer_learning_rate, ppo_loss_with_entropy_from_logits,
                     format_epoch_line)

@@ -61,6 +61,7 @@ SIGNATURES = {
     "ppo_policy_set_gemm_mode": (c_int, [vp, c_int]),
     "ppo_policy_num_params": (c_i64, [vp]),
     "ppo_batch_action_probabilities": (c_int, [vp, c_i64, c_int, PF, PF, PF]),
+    "ppo_sample_actions": (c_int, [vp, c_i64, c_int, PF, PF, c_u64, PI64, PF, PF]),
     "ppo_adam_create": (c_int, [vp, c_dbl, c_dbl, c_dbl, c_dbl, C.POINTER(vp)]),
     "ppo_adam_destroy": (c_int, [vp]),
     "ppo_adam_set_eta": (c_int, [vp, c_dbl]),

@@ -800,12 +800,9 @@ static int upload_host_batch(ppo_policy* p, int64_t nb, int nhe, const float* fe
     return PPO_OK;
 }
 
-int ppo_batch_action_probabilities(ppo_policy* p, int64_t nb, int nhe, const float* feat, const float* mask,
-                                   float* probs_out) {
-    PPO_REQUIRE(p != nullptr && feat && mask && probs_out, "batch_action_probabilities: null argument");
+// forward + masked softmax of nb host states; the probabilities [nb][A] are left in ctx->d_scratch
+static int probabilities_to_scratch(ppo_policy* p, int64_t nb, int nhe, const float* feat, const float* mask, size_t extra_scratch) {
     ppo_ctx* ctx = p->ctx;
-    PPO_TRY(use(ctx));
-    PPO_REQUIRE(nb >= 1 && nhe >= 1, "batch_action_probabilities: nb=%lld nhe=%d", (long long)nb, nhe);
     const int A = nhe * p->dims[p->L];
     const int64_t M = nb * nhe;
     PPO_TRY(upload_host_batch(p, nb, nhe, feat, mask));
@@ -815,12 +812,40 @@ int ppo_batch_action_probabilities(ppo_policy* p, int64_t nb, int nhe, const flo
     PPO_CUDA(cudaMemsetAsync(p->hbatch.old_prob, 0x3f, (size_t)nb * 4, ctx->stream));
     PPO_TRY(ensure_workspace(p, M));
     PPO_TRY(ensure_loss_buffers(p, nb, A, 1));
-    PPO_TRY(ensure_scratch(ctx, (size_t)nb * A * 4));
+    PPO_TRY(ensure_scratch(ctx, (size_t)nb * A * 4 + extra_scratch));
     PPO_TRY(policy_forward(p, p->hbatch.feat, M));
-    PPO_TRY(launch_loss(ctx, p->act[p->L], p->hbatch.mask, p->hbatch.action, p->hbatch.old_prob, p->hbatch.adv, nb, A,
-                        0.0, 0.0, 1.0 / (double)nb, nullptr, p->d_loss_partials, p->d_loss_hist,
-                        (float*)ctx->d_scratch));
+    return launch_loss(ctx, p->act[p->L], p->hbatch.mask, p->hbatch.action, p->hbatch.old_prob, p->hbatch.adv, nb, A,
+                       0.0, 0.0, 1.0 / (double)nb, nullptr, p->d_loss_partials, p->d_loss_hist, (float*)ctx->d_scratch);
+}
+
+int ppo_batch_action_probabilities(ppo_policy* p, int64_t nb, int nhe, const float* feat, const float* mask,
+                                   float* probs_out) {
+    PPO_REQUIRE(p != nullptr && feat && mask && probs_out, "batch_action_probabilities: null argument");
+    ppo_ctx* ctx = p->ctx;
+    PPO_TRY(use(ctx));
+    PPO_REQUIRE(nb >= 1 && nhe >= 1, "batch_action_probabilities: nb=%lld nhe=%d", (long long)nb, nhe);
+    const int A = nhe * p->dims[p->L];
+    PPO_TRY(probabilities_to_scratch(p, nb, nhe, feat, mask, 0));
     PPO_TRY(d2h(ctx, probs_out, ctx->d_scratch, (size_t)nb * A * 4));
+    PPO_CUDA(cudaStreamSynchronize(ctx->stream));
+    return PPO_OK;
+}
+
+int ppo_sample_actions(ppo_policy* p, int64_t nb, int nhe, const float* feat, const float* mask, uint64_t seed,
+                       int64_t* action1_out, float* prob_out, float* probs_out) {
+    PPO_REQUIRE(p != nullptr && feat && mask && action1_out && prob_out, "sample_actions: null argument");
+    ppo_ctx* ctx = p->ctx;
+    PPO_TRY(use(ctx));
+    PPO_REQUIRE(nb >= 1 && nhe >= 1, "sample_actions: nb=%lld nhe=%d", (long long)nb, nhe);
+    const int A = nhe * p->dims[p->L];
+    const size_t pbytes = round_up((int64_t)nb * A * 4, 16);
+    PPO_TRY(probabilities_to_scratch(p, nb, nhe, feat, mask, (size_t)nb * 16 + 32));
+    int64_t* d_act = (int64_t*)((char*)ctx->d_scratch + pbytes);
+    float* d_prob = (float*)((char*)ctx->d_scratch + pbytes + (size_t)nb * 8);
+    PPO_TRY(launch_sample_actions(ctx, (const float*)ctx->d_scratch, nb, A, seed, d_act, d_prob));
+    PPO_TRY(d2h(ctx, action1_out, d_act, (size_t)nb * 8));
+    PPO_TRY(d2h(ctx, prob_out, d_prob, (size_t)nb * 4));
+    if (probs_out) PPO_TRY(d2h(ctx, probs_out, ctx->d_scratch, (size_t)nb * A * 4));
     PPO_CUDA(cudaStreamSynchronize(ctx->stream));
     return PPO_OK;
 }

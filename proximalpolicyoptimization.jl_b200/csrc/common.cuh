@@ -190,6 +190,9 @@ int launch_loss(ppo_ctx* ctx, const float* logits, const float* mask, const int*
                 double* loss_out2 /* {ppoloss, entropyloss unweighted} */, float* probs_out,
                 const int* step = nullptr /* optional device scalar: write to loss_out2 + 2 * (*step) */);
 
+int launch_sample_actions(ppo_ctx* ctx, const float* probs, int64_t nb, int A, uint64_t seed, int64_t* action1,
+                          float* prob_out);
+
 // gemm_simt.cu (K5/K7, fp32 reference path) + skinny last layer
 int launch_linear_fwd_simt(ppo_ctx* ctx, const float* X, const float* W, const float* bias, float* Y,
                            int64_t M, int K, int N, bool act, float slope);

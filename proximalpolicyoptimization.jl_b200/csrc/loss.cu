@@ -299,4 +299,43 @@ int launch_loss(ppo_ctx* ctx, const float* logits, const float* mask, const int*
     return PPO_OK;
 }
 
+
+// ---- batched rollout inference -------------------------------------------------------
+// One categorical draw per state by inverse CDF over the probabilities the softmax kernel produced, as
+// `rand(Categorical(ap))` does for one state on the host (reference src/collect_rollouts.jl:5-7): sequential Float32
+// cumulative sum, first index whose cumulative probability exceeds the Float32 uniform draw.  The draw of state i is
+// output i of the splitmix64 stream of `seed` (counter-based: s_i = seed + (i + 1) * golden), top 24 bits.
+// Masked actions have probability exactly 0 and can never be returned: if rounding leaves the total below the draw,
+// the last action with non-zero probability is returned.
+__global__ void __launch_bounds__(128)
+sample_actions_kernel(const float* __restrict__ probs, int64_t nb, int A, uint64_t seed, int64_t* __restrict__ action1,
+                      float* __restrict__ prob_out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nb) return;
+    uint64_t z = seed + (uint64_t)(i + 1) * 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z ^= z >> 31;
+    const float u = (float)(z >> 40) * (1.0f / 16777216.0f);
+    const float* p = probs + i * A;
+    float c = p[0];
+    int a = 0, last = p[0] > 0.0f ? 0 : -1;
+    while (c <= u && a < A - 1) {
+        ++a;
+        const float pa = p[a];
+        c = __fadd_rn(c, pa);
+        if (pa > 0.0f) last = a;
+    }
+    if (!(p[a] > 0.0f)) a = last < 0 ? a : last;
+    action1[i] = (int64_t)a + 1;
+    prob_out[i] = p[a];
+}
+
+int launch_sample_actions(ppo_ctx* ctx, const float* probs, int64_t nb, int A, uint64_t seed, int64_t* action1, float* prob_out) {
+    sample_actions_kernel<<<(unsigned)ceil_div(nb, 128), 128, 0, ctx->stream>>>(probs, nb, A, seed, action1, prob_out);
+    ctx->launches += 1;
+    PPO_CUDA(cudaGetLastError());
+    return PPO_OK;
+}
+
 }  // namespace ppo

@@ -144,7 +144,9 @@ end
 
 dense_layers(model) = [l for l in model.layers if l isa Dense]
 
-function DevicePolicy(ctx::Context, model; leaky_slope = 0.01f0, gemm_mode = 1)
+# gemm_mode: 0 = fp32 FFMA, 1 = 3xTF32 tcgen05, 3 = scaled fp16 hi/lo pairs on tcgen05 (fastest fp32-parity engine;
+# needs in % 8 == 0, hidden widths % 32 == 0, <= 4 actions per token; refused loudly otherwise)
+function DevicePolicy(ctx::Context, model; leaky_slope = 0.01f0, gemm_mode = 3)
     ls = dense_layers(model)
     dims = Cint[size(ls[1].weight, 2); [size(l.weight, 1) for l in ls]]
     Ws = [Float32.(l.weight) for l in ls]; bs = [Float32.(l.bias) for l in ls]
@@ -168,6 +170,18 @@ function pull_weights!(p::DevicePolicy)
     for (l, W, b) in zip(ls, Ws, bs)
         l.weight .= W; l.bias .= b
     end
+end
+
+# Batched rollout inference (extension): collect_step_data!'s `action_probabilities` + `rand(Categorical(ap))`
+# (src/collect_rollouts.jl:1-15) for nb states at once.  vertex_score [nf, nhe, nb], action_mask [A, nb].
+function batch_sample_actions(p::DevicePolicy, vertex_score::Array{Float32,3}, action_mask::Matrix{Float32};
+                              seed::UInt64 = rand(UInt64))
+    nhe, nb = size(vertex_score, 2), size(vertex_score, 3)
+    actions = Vector{Int64}(undef, nb); probs = Vector{Float32}(undef, nb)
+    check(ccall((:ppo_sample_actions, lib), Cint,
+                (Ptr{Cvoid}, Int64, Cint, Ptr{Float32}, Ptr{Float32}, UInt64, Ptr{Int64}, Ptr{Float32}, Ptr{Float32}),
+                p.h, nb, nhe, vertex_score, action_mask, seed, actions, probs, C_NULL))
+    return actions, probs
 end
 
 mutable struct DeviceAdam

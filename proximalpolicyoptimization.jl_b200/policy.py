@@ -114,6 +114,24 @@ def batch_action_probabilities(policy, state):
     return probs
 
 
+def batch_sample_actions(policy, state, seed, return_probabilities=False):
+    """Batched rollout inference (extension): what ``collect_step_data!``
+    (src/collect_rollouts.jl:1-15) does for one state -- ``action_probabilities`` then ``rand(Categorical(ap))`` --
+    for a whole batch of states on the device.  Returns (selected_actions Int64 1-based [nb],
+    selected_action_probabilities Float32 [nb]) and, optionally, all probabilities [nb, A]."""
+    feat = np.ascontiguousarray(state.vertex_score, np.float32)
+    mask = np.ascontiguousarray(state.action_mask, np.float32)
+    nb, nhe = feat.shape[0], feat.shape[1]
+    actions = np.empty(nb, np.int64)
+    prob = np.empty(nb, np.float32)
+    probs = np.empty_like(mask) if return_probabilities else None
+    _lib.check(_lib.load().ppo_sample_actions(policy.handle, nb, nhe, _lib.ptr(feat, C.c_float), _lib.ptr(mask, C.c_float),
+                                              int(seed) & 0xFFFFFFFFFFFFFFFF, _lib.ptr(actions, C.c_int64),
+                                              _lib.ptr(prob, C.c_float),
+                                              _lib.ptr(probs, C.c_float) if probs is not None else None))
+    return (actions, prob, probs) if return_probabilities else (actions, prob)
+
+
 def action_probabilities(policy, state):
     """``PPO.action_probabilities(policy, state)`` — test/quad_game_utilities.jl:65-71 (one state)."""
     if hasattr(policy, "action_probabilities"):

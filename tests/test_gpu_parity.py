@@ -426,3 +426,46 @@ def test_cuda_graph_epoch_is_bit_identical(ctx, monkeypatch):
         pol.close(); buf.close()
     assert out["0"][0] == out["1"][0]
     assert np.array_equal(out["0"][1], out["1"][1])
+
+
+# ---- batched rollout inference ----------------------------------------------
+def test_sample_actions_matches_oracle_sampler(ctx):
+    """device categorical sampling == the oracle's restatement of rand(Categorical(ap)) on the SAME probabilities and
+    draws (bit-exact actions); the returned probability is the sampled entry; masked actions are never drawn."""
+    cfg = S.CONFIGS["t1"]
+    rng = np.random.default_rng(11)
+    nb = 3000
+    feat = rng.integers(-3, 9, (nb, cfg.nhe, cfg.nf)).astype(np.float32)
+    mask = S.make_masks(rng, nb, cfg.nhe, cfg.apa)
+    W, b = S.make_weights(cfg)
+    pol = P.Policy(cfg.nf, cfg.H, cfg.L, cfg.apa, ctx, weights=W, biases=b)
+    state = P.StateData(feat, mask)
+    act, prob, probs = P.batch_sample_actions(pol, state, 12345, return_probabilities=True)
+    np.testing.assert_array_equal(probs, P.batch_action_probabilities(pol, state))
+    want_act, want_prob = O.sample_actions_from_probs(probs, 12345)
+    np.testing.assert_array_equal(act, want_act)
+    np.testing.assert_array_equal(prob, want_prob)
+    assert np.all(np.isfinite(mask[np.arange(nb), act - 1])), "a masked action was drawn"
+    act2, _ = P.batch_sample_actions(pol, state, 12346)
+    assert np.mean(act2 != act) > 0.3          # another seed, another stream
+    pol.close()
+
+
+def test_sample_actions_follow_the_distribution(ctx):
+    """200 000 draws for one state: empirical frequencies within 5 sigma of the probabilities"""
+    cfg = S.CONFIGS["t1"]
+    rng = np.random.default_rng(12)
+    nb = 200_000
+    f1 = rng.integers(-3, 9, (1, cfg.nhe, cfg.nf)).astype(np.float32)
+    m1 = S.make_masks(rng, 1, cfg.nhe, cfg.apa)
+    W, b = S.make_weights(cfg)
+    W = [w * 3.0 for w in W]                   # a less uniform distribution
+    pol = P.Policy(cfg.nf, cfg.H, cfg.L, cfg.apa, ctx, weights=W, biases=b)
+    state = P.StateData(np.repeat(f1, nb, 0), np.repeat(m1, nb, 0))
+    act, prob, probs = P.batch_sample_actions(pol, state, 7, return_probabilities=True)
+    p = probs[0].astype(np.float64)
+    freq = np.bincount(act - 1, minlength=cfg.A) / nb
+    sigma = np.sqrt(p * (1 - p) / nb)
+    assert np.all(np.abs(freq - p) <= 5 * sigma + 1e-9), np.max(np.abs(freq - p) / (sigma + 1e-12))
+    assert np.all(freq[p == 0] == 0)
+    pol.close()

@@ -103,3 +103,20 @@ def test_golden_npz_match_oracle():
 def test_epoch_line_format():
     # src/train.jl:146
     assert O.format_epoch_line(3, 0.12345, -0.5, 1e-4) == "EPOCH : 3 \t PPO LOSS : 0.1235\t ENTROPY LOSS : -0.5000 \t LR : 1.0e-04\n"
+
+
+def test_oracle_categorical_sampler_properties():
+    """restated rand(Categorical(ap)): masked (p = 0) actions are never drawn, a one-hot row always returns its action
+    (the TestEnv policy of test/test_rollout_buffer.jl:24-29 has probabilities [1, 0, 0] -> action 1), and the
+    frequencies follow the probabilities"""
+    from oracle import ppo_oracle as O
+    probs = np.tile(np.array([[1.0, 0.0, 0.0]], np.float32), (50, 1))
+    act, pr = O.sample_actions_from_probs(probs, 3)
+    assert np.all(act == 1) and np.all(pr == 1.0)
+    p = np.array([0.0, 0.25, 0.0, 0.5, 0.25, 0.0], np.float32)
+    act, pr = O.sample_actions_from_probs(np.tile(p, (20000, 1)), 9)
+    freq = np.bincount(act - 1, minlength=6) / 20000
+    assert freq[0] == freq[2] == freq[5] == 0
+    assert np.all(np.abs(freq - p) < 0.02)
+    u = O.sample_uniforms(1, 1000)
+    assert u.dtype == np.float32 and u.min() >= 0.0 and u.max() < 1.0
