@@ -121,12 +121,16 @@ struct KK16Params {
     float rz_comp;
 };
 
-template <int BN>
+// TWO: a CTA pair (one cluster) shares one UMMA of M = 256 (cta_group::2): each CTA stages its own 128 rows of A and
+// HALF of the B tile, so the operand bytes per SM and MMA cycle drop from 64 to 43 B/clk (the L2 -> SM feed is what
+// bounds the single-CTA kernel at K = 512)
+template <int BN, bool TWO = false>
 struct KK16Smem {
-    static constexpr int B_TILE_BYTES = BN * F_BK * 2;
+    static constexpr int B_ROWS = TWO ? BN / 2 : BN;    // rows of the B tile this CTA stages
+    static constexpr int B_TILE_BYTES = B_ROWS * F_BK * 2;
     static constexpr int STAGE_BYTES = 2 * FA_TILE_BYTES + 2 * B_TILE_BYTES;
-    static constexpr int NST = BN > 128 ? 2 : 3;        // operand pipeline stages (96 KB / 64 KB each)
-    static constexpr int NACC = BN > 128 ? 2 : 4;       // TMEM accumulator stages (all 512 columns in use)
+    static constexpr int NST = (BN > 128 && !TWO) ? 2 : 3;   // operand pipeline stages (96 KB / 64 KB each)
+    static constexpr int NACC = BN > 128 ? 2 : 4;            // TMEM accumulator stages (all 512 columns in use)
     // every epilogue warp stages its own 32 rows x 16 columns of hi and of lo (2 x 1 KB) and issues its own TMA
     // stores: no cross-warp barrier in the epilogue, and the hi / lo buffers alternate so that a store's smem read
     // overlaps the conversion of the other half
@@ -187,13 +191,13 @@ __device__ __forceinline__ void colsum16(const float* v, int lane, float& out, i
     cidx = (b4 ? 8 : 0) + (b3 ? 4 : 0) + (b2 ? 2 : 0) + (b1 ? 1 : 0);
 }
 
-template <int BN>
+template <int BN, bool TWO>
 __global__ void __launch_bounds__(F_KK_THREADS, 1)
 f16_gemm_kk_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                    const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
                    const __grid_constant__ CUtensorMap tmC_hi, const __grid_constant__ CUtensorMap tmC_lo,
                    const KK16Params p) {
-    using S = KK16Smem<BN>;
+    using S = KK16Smem<BN, TWO>;
     constexpr int CPT = BN / 4;   // columns per epilogue thread
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -207,19 +211,28 @@ f16_gemm_kk_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + NACC);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int num_tiles = p.tiles_m * p.tiles_n;
+    // work units: single-CTA mode = 128 x BN tiles over the grid; pair mode = 256 x BN tiles over the clusters, CTA rank r
+    // of the pair owning rows [128 r, 128 r + 128) of the unit (an odd last m-tile leaves rank 1 a fully out-of-range
+    // tile: TMA zero-fills its loads and clips its stores)
+    const int rank = TWO ? (int)cluster_ctarank() : 0;
+    const int unit0 = TWO ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int unit_step = TWO ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    const int num_tiles = (TWO ? (p.tiles_m + 1) / 2 : p.tiles_m) * p.tiles_n;
     const int chunks_per_tile = (p.k_blocks + p.chunk_kb - 1) / p.chunk_kb;
+    auto m_tile_of = [&](int unit) -> int { return TWO ? 2 * (unit / p.tiles_n) + rank : unit / p.tiles_n; };
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < NST; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
-        for (int a = 0; a < NACC; ++a) { mbar_init(tfull + a, 1); mbar_init(tempty + a, F_KK_EPI_THREADS); }
+        // pair mode: one arrival per epilogue WARP of both CTAs, all on the leader's barrier
+        for (int a = 0; a < NACC; ++a) { mbar_init(tfull + a, 1); mbar_init(tempty + a, TWO ? 2 * (F_KK_EPI_THREADS / 32) : F_KK_EPI_THREADS); }
         fence_barrier_init();
         tma_prefetch_desc(&tmA_hi); tma_prefetch_desc(&tmA_lo); tma_prefetch_desc(&tmB_hi); tma_prefetch_desc(&tmB_lo);
         tma_prefetch_desc(&tmC_hi); tma_prefetch_desc(&tmC_lo);
     }
-    if (warp == 1) tmem_alloc(tmem_slot, NACC * BN);
+    if (warp == 1) { if (TWO) tmem_alloc_2sm(tmem_slot, NACC * BN); else tmem_alloc(tmem_slot, NACC * BN); }
     tc_fence_before();
     __syncthreads();
+    if (TWO) cluster_sync_all();      // the peer's barriers are initialised before anything arrives on them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -227,28 +240,39 @@ f16_gemm_kk_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
         // ===================== TMA producer =====================
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                const int m0 = (tile / p.tiles_n) * F_BM, n0 = (tile % p.tiles_n) * BN;
+            for (int tile = unit0; tile < num_tiles; tile += unit_step) {
+                const int m0 = m_tile_of(tile) * F_BM, n0 = (tile % p.tiles_n) * BN;
                 for (int kb = 0; kb < p.k_blocks; ++kb) {
                     mbar_wait(empty + stage, phase ^ 1);
                     unsigned char* st = smem + stage * S::STAGE_BYTES;
-                    mbar_expect_tx(full + stage, (uint32_t)S::STAGE_BYTES);
                     const int k0 = kb * F_BK;
-                    tma_load_2d(st, &tmA_hi, k0, m0, full + stage);
-                    tma_load_2d(st + FA_TILE_BYTES, &tmA_lo, k0, m0, full + stage);
-                    tma_load_2d(st + 2 * FA_TILE_BYTES, &tmB_hi, k0, n0, full + stage);
-                    tma_load_2d(st + 2 * FA_TILE_BYTES + S::B_TILE_BYTES, &tmB_lo, k0, n0, full + stage);
+                    if (TWO) {
+                        // the leader's barrier counts the bytes of both CTAs (its own expect_tx may come after the
+                        // peer's first complete_tx: the phase cannot end before the leader's arrival)
+                        if (rank == 0) mbar_expect_tx(full + stage, 2u * (uint32_t)S::STAGE_BYTES);
+                        const int nb0 = n0 + rank * (BN / 2);
+                        tma_load_2d_2sm(st, &tmA_hi, k0, m0, full + stage);
+                        tma_load_2d_2sm(st + FA_TILE_BYTES, &tmA_lo, k0, m0, full + stage);
+                        tma_load_2d_2sm(st + 2 * FA_TILE_BYTES, &tmB_hi, k0, nb0, full + stage);
+                        tma_load_2d_2sm(st + 2 * FA_TILE_BYTES + S::B_TILE_BYTES, &tmB_lo, k0, nb0, full + stage);
+                    } else {
+                        mbar_expect_tx(full + stage, (uint32_t)S::STAGE_BYTES);
+                        tma_load_2d(st, &tmA_hi, k0, m0, full + stage);
+                        tma_load_2d(st + FA_TILE_BYTES, &tmA_lo, k0, m0, full + stage);
+                        tma_load_2d(st + 2 * FA_TILE_BYTES, &tmB_hi, k0, n0, full + stage);
+                        tma_load_2d(st + 2 * FA_TILE_BYTES + S::B_TILE_BYTES, &tmB_lo, k0, n0, full + stage);
+                    }
                     if (++stage == NST) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer (one thread) =====================
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc_f16(F_BM, BN, 0, 0);
+        // ===================== MMA issuer (one thread; in pair mode the leader CTA's) =====================
+        if (lane == 0 && rank == 0) {
+            constexpr uint32_t idesc = make_idesc_f16(TWO ? 2 * F_BM : F_BM, BN, 0, 0);
             int stage = 0; uint32_t phase = 0;
             uint32_t cc = 0;   // accumulation chains issued so far
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            for (int tile = unit0; tile < num_tiles; tile += unit_step) {
                 for (int kb = 0; kb < p.k_blocks; ++cc) {
                     const int acc = (int)(cc % (uint32_t)NACC);
                     mbar_wait(tempty + acc, ((cc / (uint32_t)NACC) & 1u) ^ 1u);
@@ -266,12 +290,23 @@ f16_gemm_kk_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
 #pragma unroll
                         for (int k = 0; k < F_BK / 16; ++k) {
                             const uint64_t koff = (uint64_t)(k * 2);   // 16 fp16 = 32 bytes = 2 x 16 B
-                            umma_f16(d_tmem, a_lo + koff, b_hi + koff, idesc, (kc | k) != 0 ? 1u : 0u);
-                            umma_f16(d_tmem, a_hi + koff, b_lo + koff, idesc, 1u);
-                            umma_f16(d_tmem, a_hi + koff, b_hi + koff, idesc, 1u);
+                            if (TWO) {
+                                umma_f16_2sm(d_tmem, a_lo + koff, b_hi + koff, idesc, (kc | k) != 0 ? 1u : 0u);
+                                umma_f16_2sm(d_tmem, a_hi + koff, b_lo + koff, idesc, 1u);
+                                umma_f16_2sm(d_tmem, a_hi + koff, b_hi + koff, idesc, 1u);
+                            } else {
+                                umma_f16(d_tmem, a_lo + koff, b_hi + koff, idesc, (kc | k) != 0 ? 1u : 0u);
+                                umma_f16(d_tmem, a_hi + koff, b_lo + koff, idesc, 1u);
+                                umma_f16(d_tmem, a_hi + koff, b_hi + koff, idesc, 1u);
+                            }
                         }
-                        tc_commit(empty + stage);            // frees the smem slot when these MMAs retire
-                        if (kb == kb_end - 1) tc_commit(tfull + acc);
+                        if (TWO) {       // both CTAs' producers / epilogues are released by the same commit
+                            tc_commit_2sm(empty + stage, (uint16_t)3);
+                            if (kb == kb_end - 1) tc_commit_2sm(tfull + acc, (uint16_t)3);
+                        } else {
+                            tc_commit(empty + stage);            // frees the smem slot when these MMAs retire
+                            if (kb == kb_end - 1) tc_commit(tfull + acc);
+                        }
                         if (++stage == NST) { stage = 0; phase ^= 1; }
                     }
                 }
@@ -288,8 +323,10 @@ f16_gemm_kk_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
         const float unscale = __ldg(p.sc_a + 1) * __ldg(p.sc_b + 1);
         const float cscale = __ldg(p.sc_c);
         uint32_t cc = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-            const int m0 = (tile / p.tiles_n) * F_BM, n0 = (tile % p.tiles_n) * BN;
+        for (int tile = unit0; tile < num_tiles; tile += unit_step) {
+            const int mt = m_tile_of(tile);
+            const bool mt_valid = mt < p.tiles_m;
+            const int m0 = mt * F_BM, n0 = (tile % p.tiles_n) * BN;
             const int row = m0 + row_in_tile;
             float s[CPT];
 #pragma unroll
@@ -311,7 +348,12 @@ f16_gemm_kk_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
                 drain_chunk16_narrow<CPT>(tmem_base + (uint32_t)(acc * BN + cq * CPT) + ((uint32_t)(q * 32) << 16), s,
                                           1.0f + p.rz_comp * (float)(3 * (F_BK / 16) * kb_in_chunk));
                 tc_fence_before();
-                mbar_arrive(tempty + acc);
+                if (TWO) {
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_leader(tempty + acc);
+                } else {
+                    mbar_arrive(tempty + acc);
+                }
             }
             // ---- unscale, bias / activation (or gradient gate), rescale, fp16 split, staged TMA store (16 columns at a time)
 #pragma unroll
@@ -342,7 +384,7 @@ f16_gemm_kk_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
                             v[j] = (p.act && !pos) ? p.slope * x : x;
                         }
                     }
-                    if (p.signs_out != nullptr && col0 < p.N) p.signs_out[sign_index(row, col0 >> 5, p.N >> 5)] = w;
+                    if (p.signs_out != nullptr && col0 < p.N && mt_valid) p.signs_out[sign_index(row, col0 >> 5, p.N >> 5)] = w;
                 } else {
                     const float inb = (row < p.M) ? unscale : 0.0f;     // rows beyond M: keep them out of the column sums
                     const float ins = inb * p.slope;
@@ -357,8 +399,8 @@ f16_gemm_kk_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
                         // = the bias gradient of the layer below, fused here so that dX is never re-read for it
                         float cs; int cidx;
                         colsum16(vv, lane, cs, cidx);
-                        if ((lane & 1) == 0 && col0 + 16 * hh + cidx < p.N)
-                            p.colsum_partial[((size_t)(tile / p.tiles_n) * 4 + q) * p.N + col0 + 16 * hh + cidx] = cs;
+                        if ((lane & 1) == 0 && col0 + 16 * hh + cidx < p.N && mt_valid)
+                            p.colsum_partial[((size_t)mt * 4 + q) * p.N + col0 + 16 * hh + cidx] = cs;
                     }
                     uint4 h[2], l[2];
 #pragma unroll
@@ -390,7 +432,8 @@ f16_gemm_kk_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem_base, NACC * BN);
+    if (TWO) cluster_sync_all();      // neither CTA leaves while the pair's MMAs / commits may still touch the other
+    if (warp == 1) { if (TWO) tmem_dealloc_2sm(tmem_base, NACC * BN); else tmem_dealloc(tmem_base, NACC * BN); }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1050,14 +1093,14 @@ int launch_split16(ppo_ctx* ctx, const float* x, __half* hi, __half* lo, int64_t
     return PPO_OK;
 }
 
-template <int BN>
+template <int BN, bool TWO>
 int launch_kk16(ppo_ctx* ctx, const __half* A, const __half* A_lo, const __half* B, const __half* B_lo, __half* C, __half* C_lo,
                 int64_t M, int N, int K, const KK16Params& base) {
     CUtensorMap mA, mAl, mB, mBl, mC, mCl;
     PPO_TRY(make_map16_2d(&mA, A, M, K, F_BM));
     PPO_TRY(make_map16_2d(&mAl, A_lo, M, K, F_BM));
-    PPO_TRY(make_map16_2d(&mB, B, N, K, BN));
-    PPO_TRY(make_map16_2d(&mBl, B_lo, N, K, BN));
+    PPO_TRY(make_map16_2d(&mB, B, N, K, KK16Smem<BN, TWO>::B_ROWS));
+    PPO_TRY(make_map16_2d(&mBl, B_lo, N, K, KK16Smem<BN, TWO>::B_ROWS));
     PPO_TRY(make_map16_2d(&mC, C, M, N, 32, 16));      // store boxes: 32 rows x 16 columns (one warp's), SWIZZLE_32B
     PPO_TRY(make_map16_2d(&mCl, C_lo, M, N, 32, 16));
     KK16Params p = base;
@@ -1067,11 +1110,33 @@ int launch_kk16(ppo_ctx* ctx, const __half* A, const __half* A_lo, const __half*
     p.rz_comp = env_comp >= 0.0f ? env_comp : F_RZ_COMP;
     p.M = (int)M; p.N = N; p.K = K;
     p.tiles_m = (int)ceil_div(M, F_BM); p.tiles_n = (int)ceil_div(N, BN); p.k_blocks = (int)ceil_div(K, F_BK);
-    const int tiles = p.tiles_m * p.tiles_n;
-    const int grid = std::min(tiles, ctx->num_sms);
-    const size_t smem = KK16Smem<BN>::TOTAL;
-    PPO_CUDA(cudaFuncSetAttribute(f16_gemm_kk_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    f16_gemm_kk_kernel<BN><<<grid, F_KK_THREADS, smem, ctx->stream>>>(mA, mAl, mB, mBl, mC, mCl, p);
+    const size_t smem = KK16Smem<BN, TWO>::TOTAL;
+    PPO_CUDA(cudaFuncSetAttribute(f16_gemm_kk_kernel<BN, TWO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (TWO) {
+        const int units = ((p.tiles_m + 1) / 2) * p.tiles_n;
+        cudaLaunchConfig_t cfg{};
+        cfg.blockDim = dim3(F_KK_THREADS);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = ctx->stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        // persistent pairs: as many clusters as can be co-resident (an SM without a free partner in its TPC stays idle)
+        static int max_clusters = 0;
+        if (max_clusters == 0) {
+            cfg.gridDim = dim3((unsigned)(2 * (ctx->num_sms / 2)));
+            int nc = 0;
+            PPO_CUDA(cudaOccupancyMaxActiveClusters(&nc, f16_gemm_kk_kernel<BN, TWO>, &cfg));
+            max_clusters = std::max(1, std::min(nc, ctx->num_sms / 2));
+        }
+        cfg.gridDim = dim3((unsigned)(2 * std::min(units, max_clusters)));
+        PPO_CUDA(cudaLaunchKernelEx(&cfg, f16_gemm_kk_kernel<BN, TWO>, mA, mAl, mB, mBl, mC, mCl, p));
+    } else {
+        const int tiles = p.tiles_m * p.tiles_n;
+        const int grid = std::min(tiles, ctx->num_sms);
+        f16_gemm_kk_kernel<BN, TWO><<<grid, F_KK_THREADS, smem, ctx->stream>>>(mA, mAl, mB, mBl, mC, mCl, p);
+    }
     ctx->launches += 1;
     PPO_CUDA(cudaGetLastError());
     return PPO_OK;
@@ -1086,8 +1151,12 @@ int kk16_dispatch(ppo_ctx* ctx, const __half* A, const __half* A_lo, const __hal
     // it off the critical path (measured 0.56 vs 0.66 ms at M = 2^20, K = 64, N = 512)
     static const int force128 = getenv("PPO_F16_BN128") ? atoi(getenv("PPO_F16_BN128")) : -1;   // tuning experiments
     const bool wide = force128 >= 0 ? !force128 : (K > 128);
-    if (N > 128 && wide) return launch_kk16<256>(ctx, A, A_lo, B, B_lo, C, C_lo, M, N, K, base);
-    return launch_kk16<128>(ctx, A, A_lo, B, B_lo, C, C_lo, M, N, K, base);
+    // CTA pairs (cta_group::2) halve the weight-tile bytes per SM: 1.35 vs 1.43 ms at M = 2^20, K = N = 512
+    static const int pair_env = getenv("PPO_F16_2SM") ? atoi(getenv("PPO_F16_2SM")) : -1;         // tuning experiments
+    const bool pair = pair_env >= 0 ? pair_env != 0 : (M > F_BM);
+    if (N > 128 && wide && pair) return launch_kk16<256, true>(ctx, A, A_lo, B, B_lo, C, C_lo, M, N, K, base);
+    if (N > 128 && wide) return launch_kk16<256, false>(ctx, A, A_lo, B, B_lo, C, C_lo, M, N, K, base);
+    return launch_kk16<128, false>(ctx, A, A_lo, B, B_lo, C, C_lo, M, N, K, base);
 }
 
 template <int BN>
