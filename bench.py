@@ -210,7 +210,7 @@ def _run_ours(args):
         dist.init_process_group("cpu:gloo,cuda:nccl", rank=rank, world_size=world)
     torch.cuda.set_device(local_rank)
     cfg = S.CONFIGS[args.config]
-    B_local = max(1, cfg.B // world)
+    B_local = max(1, (args.batch or cfg.B) // world)
     ctx = P.Context(local_rank)
     if world > 1:
         D.init_comm(ctx)
@@ -427,6 +427,8 @@ def main():
                     help="only the warm-up + timed resident steps (for ncu launch lists): no data-generation forward, "
                          "no per-kernel hooks, no CPU baseline")
     ap.add_argument("--config", default="c3")
+    ap.add_argument("--batch", type=int, default=0,
+                    help="override the global minibatch size (profiling the small-minibatch regime of the N-GPU runs on one GPU)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

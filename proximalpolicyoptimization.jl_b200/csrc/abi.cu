@@ -227,7 +227,12 @@ int step_core(ppo_policy* p, ppo_opt* opt, const ppo_batch& bt, int64_t nb, int 
                         inv_nb_global, p->dlogits, p->d_loss_partials, p->d_loss_hist + (d_step ? 0 : 2 * slot), nullptr,
                         d_step));
     PPO_TRY(policy_backward(p, bt.feat, M));
-    if (ctx->nccl_comm != nullptr && ctx->nranks > 1) PPO_TRY(nccl_allreduce_f32(ctx, p->grads, p->P));
+    if (ctx->nccl_comm != nullptr && ctx->nranks > 1) {
+        // the fp16-split engine all-reduces every layer's gradient as soon as it is complete (overlapped with the rest of
+        // the backward pass); the other engines reduce the whole flat vector here
+        if (p->gemm_mode == PPO_GEMM_F16X3_TC && dp_overlap(ctx)) PPO_TRY(grads_join(ctx));
+        else PPO_TRY(nccl_allreduce_f32(ctx, p->grads, p->P));
+    }
     if (opt != nullptr) {
         PPO_TRY(launch_adam(ctx, p->params, opt->m, opt->v, p->grads, p->P, opt->eta, opt->beta1, opt->beta2,
                             opt->eps, opt->d_bp, 1.0f));
@@ -371,6 +376,9 @@ int ppo_ctx_destroy(ppo_ctx* ctx) {
     if (ctx->d_scratch) cudaFree(ctx->d_scratch);
     if (ctx->d_flush) cudaFree(ctx->d_flush);
     if (ctx->d_step) cudaFree(ctx->d_step);
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+    if (ctx->comm_stream) cudaStreamDestroy(ctx->comm_stream);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     cudaStreamDestroy(ctx->stream);
     delete ctx;

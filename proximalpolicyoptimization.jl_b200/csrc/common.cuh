@@ -61,6 +61,11 @@ struct ppo_ctx {
     int* d_step = nullptr;           // device-side minibatch counter (CUDA-graph replay of the epoch loop)
     void* nccl_comm = nullptr;
     int nranks = 1, rank = 0;
+    // data parallelism: the gradient all-reduce runs layer by layer on a second stream while the backward pass of the
+    // layers below is still computing (fork: ev_fork recorded on `stream`; join: `stream` waits for ev_join)
+    cudaStream_t comm_stream = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    bool comm_pending = false;
     static constexpr int PINNED_DOUBLES = 1 << 16;
 };
 
@@ -218,6 +223,14 @@ int nccl_unique_id(void* id128);
 int nccl_init(ppo_ctx* ctx, int nranks, int rank, const void* id128);
 int nccl_destroy(ppo_ctx* ctx);
 int nccl_allreduce_f32(ppo_ctx* ctx, float* d_buf, int64_t n);
+int nccl_allreduce_f32_on(ppo_ctx* ctx, float* d_buf, int64_t n, cudaStream_t stream);
+// overlapped gradient all-reduce (no-ops without a communicator): grads_ready enqueues the all-reduce of a finished
+// slice of the gradient vector on the communication stream, ordered after everything enqueued on ctx->stream so far;
+// grads_join makes ctx->stream wait for all of them (call before the optimiser).  Returns true from dp_overlap() when the
+// engine should use them instead of one all-reduce after the whole backward pass.
+bool dp_overlap(ppo_ctx* ctx);
+int grads_ready(ppo_ctx* ctx, float* d_slice, int64_t n);
+int grads_join(ppo_ctx* ctx);
 int nccl_allreduce_f64(ppo_ctx* ctx, double* d_buf, int64_t n);
 
 // l2 flush helper

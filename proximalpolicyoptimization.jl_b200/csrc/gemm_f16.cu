@@ -622,31 +622,43 @@ struct F16LayerTable {
     long long w_off[F_MAX_LAYERS], b_off[F_MAX_LAYERS];
 };
 
-// stats[l][0..3] = {max |W|, max_n sum_k |W[k][n]|, max_k sum_n |W[k][n]|, max |b|}; grid (blocks, L)
+// stats[l][0..3] = {max |W|, max_n sum_k |W[k][n]|, max_k sum_n |W[k][n]|, max |b|}; grid (blocks, L).
+// Column blocks: 256 threads = 32 columns x 8 row groups (coalesced 128-byte rows, 8 partial sums per column folded in
+// a fixed order); row blocks: one warp per row, lanes stride over the columns, fixed-order shuffle fold.  All maxima go
+// through atomicMax on the bit pattern (order-independent), so the statistics are deterministic.
 __global__ void __launch_bounds__(256)
 wstats_kernel(const float* __restrict__ params, F16LayerTable t, unsigned* stats) {
+    __shared__ float part[8][33];
     const int l = blockIdx.y;
     const int K = t.K[l], N = t.N[l];
-    const int nbc = (N + 255) / 256, nbr = (K + 255) / 256;
+    const int nbc = (N + 31) / 32, nbr = (K + 7) / 8;
     if ((int)blockIdx.x >= nbc + nbr) return;
     const float* W = params + t.w_off[l];
     const float* b = params + t.b_off[l];
+    const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
     float amax = 0.0f, colmax = 0.0f, rowmax = 0.0f, bmax = 0.0f;
     if ((int)blockIdx.x < nbc) {
-        const int n = blockIdx.x * 256 + threadIdx.x;
-        if (n < N) {
-            float s = 0.0f;
-            for (int k = 0; k < K; ++k) { const float a = fabsf(W[(size_t)k * N + n]); s += a; amax = fmaxf(amax, a); }
-            colmax = s;
+        const int n = blockIdx.x * 32 + lane;
+        float s = 0.0f;
+        if (n < N)
+            for (int k = grp; k < K; k += 8) { const float a = fabsf(W[(size_t)k * N + n]); s += a; amax = fmaxf(amax, a); }
+        part[grp][lane] = s;
+        __syncthreads();
+        if (grp == 0 && n < N) {
+            float c = 0.0f;
+#pragma unroll
+            for (int g = 0; g < 8; ++g) c += part[g][lane];
+            colmax = c;
             bmax = fabsf(b[n]);
         }
     } else {
-        const int k = (blockIdx.x - nbc) * 256 + threadIdx.x;
-        if (k < K) {
-            float s = 0.0f;
-            for (int n = 0; n < N; ++n) s += fabsf(W[(size_t)k * N + n]);
-            rowmax = s;
-        }
+        const int k = (blockIdx.x - nbc) * 8 + grp;
+        float s = 0.0f;
+        if (k < K)
+            for (int n = lane; n < N; n += 32) s += fabsf(W[(size_t)k * N + n]);
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+        rowmax = s;
     }
     amax = block_max_256(amax); colmax = block_max_256(colmax); rowmax = block_max_256(rowmax); bmax = block_max_256(bmax);
     if (threadIdx.x == 0) {
@@ -767,16 +779,42 @@ weight_prep16_kernel(const float* __restrict__ W, __half* __restrict__ W_hi, __h
     }
 }
 
-// out[i] = (sum_z partial[z*stride + i]) * inv(sa) * inv(sb), fixed order
+// out[i] = (sum_z partial[z*stride + i]) * inv(sa) * inv(sb); fixed order: four interleaved chains over z (independent
+// loads in flight), folded as (s0 + s1) + (s2 + s3)
 __global__ void __launch_bounds__(256)
 f16_reduce_kernel(const float* __restrict__ partial, int splits, int64_t stride, int64_t count, float* __restrict__ out,
                   const float* sa, const float* sb) {
     const float u = (sa ? __ldg(sa + 1) : 1.0f) * (sb ? __ldg(sb + 1) : 1.0f);
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x) {
-        float s = 0.0f;
-        for (int z = 0; z < splits; ++z) s += partial[(size_t)z * stride + i];
-        out[i] = s * u;
+        float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
+        int z = 0;
+        for (; z + 3 < splits; z += 4) {
+            s0 += partial[(size_t)z * stride + i];
+            s1 += partial[(size_t)(z + 1) * stride + i];
+            s2 += partial[(size_t)(z + 2) * stride + i];
+            s3 += partial[(size_t)(z + 3) * stride + i];
+        }
+        for (; z < splits; ++z) s0 += partial[(size_t)z * stride + i];
+        out[i] = ((s0 + s1) + (s2 + s3)) * u;
     }
+}
+
+// last stage of the head's partial fold: sum the `chunks` rows of scratch [chunks][K*N + N + K] and scatter the three
+// slices to dW [K*N], db [N] and (optionally) the bias gradient of the layer below [K]
+__global__ void __launch_bounds__(256)
+head_finish_kernel(const float* __restrict__ scratch, int chunks, int K, int N, float* __restrict__ dW, float* __restrict__ db,
+                   float* __restrict__ db_below) {
+    const int stride = K * N + N + K;
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= stride) return;
+    float s0 = 0.0f, s1 = 0.0f;
+    int z = 0;
+    for (; z + 1 < chunks; z += 2) { s0 += scratch[(size_t)z * stride + i]; s1 += scratch[(size_t)(z + 1) * stride + i]; }
+    if (z < chunks) s0 += scratch[(size_t)z * stride + i];
+    const float s = s0 + s1;
+    if (i < K * N) dW[i] = s;
+    else if (i < K * N + N) db[i - K * N] = s;
+    else if (db_below != nullptr) db_below[i - K * N - N] = s;
 }
 
 // stage 1 of folding the dgrad epilogue's per-quarter column sums: block (x = column block, y = row chunk)
@@ -1059,7 +1097,7 @@ int wgrad_splits16(int64_t M, int tiles, int num_sms) {
 }
 
 size_t head16_partial_bytes(int64_t M, int K, int N, int num_sms) {
-    return (size_t)head16_ctas(M, num_sms) * ((size_t)K * N + N + K) * sizeof(float);
+    return (size_t)(head16_ctas(M, num_sms) + 64) * ((size_t)K * N + N + K) * sizeof(float);   // partials + fold scratch
 }
 
 size_t f16_partial_bytes(int64_t tokens, int K, int N, int num_sms) {
@@ -1234,7 +1272,7 @@ int head_bwd16(ppo_ctx* ctx, const __half* H_hi, const __half* H_lo, const float
     const int64_t ctas = head16_ctas(M, ctx->num_sms);
     const int64_t rows = ceil_div(M, ctas);
     const int64_t stride = (int64_t)K * N + N + K;
-    PPO_REQUIRE((size_t)ctas * stride * sizeof(float) <= partial_bytes, "f16 head_bwd: partial buffer too small");
+    PPO_REQUIRE((size_t)(ctas + 64) * stride * sizeof(float) <= partial_bytes, "f16 head_bwd: partial buffer too small");
     const int need_dH = dH_hi != nullptr ? 1 : 0;
     const int rpp = 256 / (K / 4);
     const size_t smem = (size_t)rpp * stride * sizeof(float);
@@ -1246,14 +1284,16 @@ int head_bwd16(ppo_ctx* ctx, const __half* H_hi, const __half* H_lo, const float
     }
     ctx->launches += 1;
     PPO_CUDA(cudaGetLastError());
-    const int64_t cnt = (int64_t)K * N;
-    f16_reduce_kernel<<<(unsigned)ceil_div(cnt, 256), 256, 0, ctx->stream>>>(partial, (int)ctas, stride, cnt, dW, nullptr, nullptr);
-    f16_reduce_kernel<<<1, 256, 0, ctx->stream>>>(partial + cnt, (int)ctas, stride, N, db, nullptr, nullptr);
+    // fold the per-CTA partials [ctas][stride] in two parallel stages (a single pass over 592 partials per output is a
+    // 60 us serial chain: it dominated the small-minibatch regime of the multi-GPU runs)
+    const int chunks = (int)std::min<int64_t>(64, ctas);
+    const int64_t rpc = ceil_div(ctas, chunks);
+    float* scratch = partial + (size_t)ctas * stride;
+    f16_colsum_fold_kernel<<<dim3((unsigned)ceil_div(stride, 256), (unsigned)chunks), 256, 0, ctx->stream>>>(partial, ctas, (int)stride,
+                                                                                                        rpc, scratch);
+    head_finish_kernel<<<(unsigned)ceil_div(stride, 256), 256, 0, ctx->stream>>>(scratch, chunks, K, N, dW, db,
+                                                                              (db_below != nullptr && need_dH) ? db_below : nullptr);
     ctx->launches += 2;
-    if (db_below != nullptr && need_dH) {
-        f16_reduce_kernel<<<(unsigned)ceil_div(K, 256), 256, 0, ctx->stream>>>(partial + cnt + N, (int)ctas, stride, K, db_below, nullptr, nullptr);
-        ctx->launches += 1;
-    }
     PPO_CUDA(cudaGetLastError());
     return PPO_OK;
 }
@@ -1347,7 +1387,7 @@ int f16_refresh_weights(ppo_policy* p) {
     unsigned* wst = st->st + 2;
     PPO_CUDA(cudaMemsetAsync(wst, 0, (size_t)4 * L * 4, ctx->stream));
     int maxb = 1;
-    for (int l = 0; l < L; ++l) maxb = std::max(maxb, (int)(ceil_div(p->dims[l], 256) + ceil_div(p->dims[l + 1], 256)));
+    for (int l = 0; l < L; ++l) maxb = std::max(maxb, (int)(ceil_div(p->dims[l], 8) + ceil_div(p->dims[l + 1], 32)));
     wstats_kernel<<<dim3((unsigned)maxb, (unsigned)L), 256, 0, ctx->stream>>>(p->params, st->table, wst);
     plan_w_kernel<<<1, 32, 0, ctx->stream>>>(L, wst, st->sc);
     ctx->launches += 2;
@@ -1403,6 +1443,9 @@ int f16_backward(ppo_policy* p, int64_t M) {
                        st->dz_lo[pp], p->grads + p->w_off[L - 1], p->grads + p->b_off[L - 1], p->grads + p->b_off[L - 2], M,
                        p->dims[L - 1], p->dims[L], p->slope, st->partial, st->partial_bytes, st->sc + 2 * sc_act(L - 1),
                        st->sc + 2 * sc_dz(L, L - 2)));
+    // data parallelism: a layer's slice of the flat gradient vector (dW_l, db_l: contiguous in Flux.params order) is
+    // all-reduced on the communication stream as soon as it is complete, while the layers below still compute
+    PPO_TRY(grads_ready(ctx, p->grads + p->w_off[L - 1], p->P - p->w_off[L - 1]));
     for (int l = L - 2; l >= 0; --l) {
         const int K = p->dims[l], N = p->dims[l + 1];
         F16Layer& ly = st->layers[l];
@@ -1411,6 +1454,7 @@ int f16_backward(ppo_policy* p, int64_t M) {
         const float* sc_dy = st->sc + 2 * sc_dz(L, l);
         PPO_TRY(wgrad16(ctx, X_hi, X_lo, st->dz_hi[pp], st->dz_lo[pp], p->grads + p->w_off[l], st->partial, st->partial_bytes, M,
                         K, N, st->sc + 2 * sc_act(l), sc_dy));
+        PPO_TRY(grads_ready(ctx, p->grads + p->w_off[l], p->w_off[l + 1] - p->w_off[l]));      // dW_l and db_l (db_l came from above)
         if (l > 0) {
             KK16Params kp{};
             kp.epi = F_EPI_DGRAD; kp.act = 0; kp.slope = p->slope; kp.gate = st->act_sign[l];

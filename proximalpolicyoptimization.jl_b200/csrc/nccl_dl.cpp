@@ -104,6 +104,39 @@ int nccl_allreduce_f32(ppo_ctx* ctx, float* d_buf, int64_t n) {
     return PPO_OK;
 }
 
+int nccl_allreduce_f32_on(ppo_ctx* ctx, float* d_buf, int64_t n, cudaStream_t stream) {
+    PPO_REQUIRE(ctx->nccl_comm != nullptr, "no communicator");
+    PPO_NCCL(g_api.AllReduce(d_buf, d_buf, (size_t)n, ncclFloat32, ncclSum, (ncclComm_t)ctx->nccl_comm, stream));
+    return PPO_OK;
+}
+
+bool dp_overlap(ppo_ctx* ctx) {
+    static const int off = getenv("PPO_B200_NO_DP_OVERLAP") ? atoi(getenv("PPO_B200_NO_DP_OVERLAP")) : 0;
+    return ctx->nccl_comm != nullptr && ctx->nranks > 1 && !off;
+}
+
+int grads_ready(ppo_ctx* ctx, float* d_slice, int64_t n) {
+    if (!dp_overlap(ctx) || n <= 0) return PPO_OK;
+    if (ctx->comm_stream == nullptr) {
+        PPO_CUDA(cudaStreamCreateWithFlags(&ctx->comm_stream, cudaStreamNonBlocking));
+        PPO_CUDA(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+        PPO_CUDA(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
+    }
+    PPO_CUDA(cudaEventRecord(ctx->ev_fork, ctx->stream));
+    PPO_CUDA(cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_fork, 0));
+    PPO_TRY(nccl_allreduce_f32_on(ctx, d_slice, n, ctx->comm_stream));
+    ctx->comm_pending = true;
+    return PPO_OK;
+}
+
+int grads_join(ppo_ctx* ctx) {
+    if (!ctx->comm_pending) return PPO_OK;
+    PPO_CUDA(cudaEventRecord(ctx->ev_join, ctx->comm_stream));
+    PPO_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
+    ctx->comm_pending = false;
+    return PPO_OK;
+}
+
 int nccl_allreduce_f64(ppo_ctx* ctx, double* d_buf, int64_t n) {
     PPO_REQUIRE(ctx->nccl_comm != nullptr, "no communicator");
     PPO_NCCL(g_api.AllReduce(d_buf, d_buf, (size_t)n, ncclFloat64, ncclSum, (ncclComm_t)ctx->nccl_comm, ctx->stream));
