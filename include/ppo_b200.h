@@ -46,6 +46,7 @@ typedef enum {
 
 /* GEMM engine for the policy MLP (the only dense contraction, test/policy.jl:11-15). */
 typedef enum {
+    PPO_GEMM_AUTO = -1,       /* fastest fp32-parity engine whose shape contract the policy meets: F16X3, else TF32X3, else FP32 */
     PPO_GEMM_FP32_SIMT = 0,   /* fp32 FFMA tiles: bit-for-bit deterministic fp32 reference path */
     PPO_GEMM_TF32X3_TC = 1,   /* tcgen05 kind::tf32, error-compensated 3-pass split: fp32 parity */
     PPO_GEMM_BF16_TC = 2,     /* tcgen05 kind::f16 (bf16 in, fp32 accumulate): fast mode (declared, not built) */
@@ -154,6 +155,7 @@ int ppo_policy_destroy(ppo_policy* p);
 int ppo_policy_read(ppo_policy* p, float* const* W, float* const* b);
 int ppo_policy_write(ppo_policy* p, const float* const* W, const float* const* b);
 int ppo_policy_set_gemm_mode(ppo_policy* p, int mode);
+int ppo_policy_get_gemm_mode(ppo_policy* p);   /* the engine in use (after PPO_GEMM_AUTO: the one that was picked) */
 int64_t ppo_policy_num_params(ppo_policy* p);
 /* PPO.batch_action_probabilities(policy, state), test/quad_game_utilities.jl:73-79:
  * probs[nb][A] = softmax(reshape(policy(feat), :, nb) + mask). */

@@ -20,3 +20,4 @@ from .dataset import DiskDataset, load_sample, load_batch, construct_disk_datase
 from . import distributed, bson_io
 
 GEMM_FP32_SIMT, GEMM_TF32X3_TC, GEMM_BF16_TC, GEMM_F16X3_TC = 0, 1, 2, 3
+GEMM_AUTO = -1

@@ -788,6 +788,14 @@ int ppo_policy_write(ppo_policy* p, const float* const* W, const float* const* b
 int ppo_policy_set_gemm_mode(ppo_policy* p, int mode) {
     PPO_REQUIRE(p != nullptr, "null policy");
     PPO_TRY(use(p->ctx));
+    if (mode == PPO_GEMM_AUTO) {
+        // the engines refuse shapes outside their contract with PPO_ERR_INVALID and no side effect: walk down the list
+        if (f16_prepare(p) == PPO_OK) mode = PPO_GEMM_F16X3_TC;
+        else if (tc_prepare(p, PPO_GEMM_TF32X3_TC) == PPO_OK) mode = PPO_GEMM_TF32X3_TC;
+        else mode = PPO_GEMM_FP32_SIMT;
+        p->gemm_mode = mode;
+        return refresh_engine_weights(p);
+    }
     PPO_REQUIRE(mode == PPO_GEMM_FP32_SIMT || mode == PPO_GEMM_TF32X3_TC || mode == PPO_GEMM_BF16_TC ||
                 mode == PPO_GEMM_F16X3_TC, "set_gemm_mode: unknown mode %d", mode);
     if (mode == PPO_GEMM_F16X3_TC) PPO_TRY(f16_prepare(p));
@@ -795,6 +803,8 @@ int ppo_policy_set_gemm_mode(ppo_policy* p, int mode) {
     p->gemm_mode = mode;
     return refresh_engine_weights(p);
 }
+
+int ppo_policy_get_gemm_mode(ppo_policy* p) { return p ? p->gemm_mode : PPO_ERR_INVALID; }
 
 int64_t ppo_policy_num_params(ppo_policy* p) { return p ? p->P : -1; }
 

@@ -144,9 +144,10 @@ end
 
 dense_layers(model) = [l for l in model.layers if l isa Dense]
 
-# gemm_mode: 0 = fp32 FFMA, 1 = 3xTF32 tcgen05, 3 = scaled fp16 hi/lo pairs on tcgen05 (fastest fp32-parity engine;
-# needs in % 8 == 0, hidden widths % 32 == 0, <= 4 actions per token; refused loudly otherwise)
-function DevicePolicy(ctx::Context, model; leaky_slope = 0.01f0, gemm_mode = 3)
+# gemm_mode: -1 = auto (fastest fp32-parity engine whose shape contract the model meets), 0 = fp32 FFMA, 1 = 3xTF32
+# tcgen05, 3 = scaled fp16 hi/lo pairs on tcgen05 (needs in % 8 == 0, hidden widths % 32 == 0, <= 4 actions per token)
+gemm_mode(p) = ccall((:ppo_policy_get_gemm_mode, lib), Cint, (Ptr{Cvoid},), p.h)
+function DevicePolicy(ctx::Context, model; leaky_slope = 0.01f0, gemm_mode = -1)
     ls = dense_layers(model)
     dims = Cint[size(ls[1].weight, 2); [size(l.weight, 1) for l in ls]]
     Ws = [Float32.(l.weight) for l in ls]; bs = [Float32.(l.bias) for l in ls]

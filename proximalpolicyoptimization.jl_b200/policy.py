@@ -78,7 +78,14 @@ class Policy:
         _lib.check(_lib.load().ppo_policy_write(self.handle, _pp(W), _pp(b)))
 
     def set_gemm_mode(self, mode: int):
+        """GEMM engine of the MLP: GEMM_AUTO (-1) picks the fastest fp32-parity engine whose shape contract the policy
+        meets (fp16-split tcgen05, else 3xTF32 tcgen05, else fp32 FFMA); returns the engine in use."""
         _lib.check(_lib.load().ppo_policy_set_gemm_mode(self.handle, int(mode)))
+        return self.gemm_mode
+
+    @property
+    def gemm_mode(self) -> int:
+        return int(_lib.load().ppo_policy_get_gemm_mode(self.handle))
 
     def __call__(self, state):
         raise NotImplementedError("use batch_action_probabilities(policy, state)")

@@ -227,3 +227,13 @@ def test_golden_epoch_tc_mode(ctx, name, key):
     Wd, bd = pol.weights()
     assert np.max(np.abs(_flat(Wd, bd) - z["flat_after"])) <= 2e-5
     pol.close(); buf.close()
+
+
+def test_gemm_auto_picks_the_fastest_engine_inside_its_contract(ctx):
+    for key, want in (("t0", SIMT), ("t1", TC), ("c3", F16), ("c2", F16)):
+        cfg = S.CONFIGS[key]
+        W, b = S.make_weights(cfg)
+        pol = P.Policy(cfg.nf, cfg.H, cfg.L, cfg.apa, ctx, weights=W, biases=b)
+        assert pol.gemm_mode == SIMT
+        assert pol.set_gemm_mode(P.GEMM_AUTO) == want, key
+        pol.close()
