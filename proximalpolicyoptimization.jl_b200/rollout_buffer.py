@@ -41,8 +41,41 @@ def batch_state(state_data_vector):
     return StateData(vs, am)
 
 
+def pad_vertex_scores(vertex_scores_vector, num_tokens=None):
+    """``pad_vertex_scores`` — examples/triangle/distance_weighted/triangle_utilities.jl:31-37: states of meshes of
+    different size are zero-padded to the largest token (half-edge) count (or to ``num_tokens``).  Arrays are
+    [nhe_i, nf] here (= Julia [nf, nhe_i])."""
+    vs = [np.asarray(v) for v in vertex_scores_vector]
+    top = max(v.shape[0] for v in vs) if num_tokens is None else int(num_tokens)
+    assert all(v.shape[0] <= top for v in vs)
+    return [np.concatenate([v, np.zeros((top - v.shape[0],) + v.shape[1:], v.dtype)]) for v in vs]
+
+
+def pad_action_mask(action_mask_vector, num_actions=None):
+    """``pad_action_mask`` — triangle_utilities.jl:39-45: masks are padded with ``-Inf32`` (probability exactly 0)."""
+    am = [np.asarray(m, np.float32).reshape(-1) for m in action_mask_vector]
+    top = max(m.size for m in am) if num_actions is None else int(num_actions)
+    assert all(m.size <= top for m in am)
+    return [np.concatenate([m, np.full(top - m.size, -np.inf, np.float32)]) for m in am]
+
+
+def prepare_state_data_for_batching_(state_data_vector, num_tokens=None, actions_per_token=None):
+    """``PPO.prepare_state_data_for_batching!`` — triangle_utilities.jl:47-55 (in place)."""
+    vs = pad_vertex_scores([s.vertex_score for s in state_data_vector], num_tokens)
+    na = None if num_tokens is None or actions_per_token is None else int(num_tokens) * int(actions_per_token)
+    am = pad_action_mask([s.action_mask for s in state_data_vector], na)
+    state_data_vector[:] = [StateData(v, m) for v, m in zip(vs, am)]
+    return state_data_vector
+
+
 class DeviceRollouts:
     """``BufferRollouts()`` — src/rollout_buffer.jl:9-22 — on the device.
+
+    Variable-size states: the buffer has a fixed token capacity ``nhe``; ``update_`` pads smaller
+    states exactly like the reference's ``pad_vertex_scores`` / ``pad_action_mask`` (zeros / -Inf32), so the padded
+    actions have probability exactly 0 and contribute nothing to the loss or the gradients.  (Padding is to the
+    buffer's capacity instead of the largest state of each minibatch; the only visible difference is the ``s / A`` term
+    of ``smoothed_entropy`` with s = 1f-8, below Float32 resolution.)
 
     ``update_`` stages transitions in a host chunk and appends them in batches (one H2D copy per
     chunk instead of five ``push!`` per transition)."""
@@ -75,8 +108,19 @@ class DeviceRollouts:
     def update_(self, state, action_probability, action, reward, terminal):
         """``update!(episode, state, action_probability, action, reward, terminal)`` — :24-38."""
         i = self._pending
-        self._s_feat[i] = np.asarray(state.vertex_score).reshape(self.nhe, self.nf)
-        self._s_mask[i] = np.asarray(state.action_mask).reshape(self.A)
+        vs = np.asarray(state.vertex_score)
+        am = np.asarray(state.action_mask).reshape(-1)
+        if vs.size == self.nhe * self.nf and am.size == self.A:
+            self._s_feat[i] = vs.reshape(self.nhe, self.nf)
+            self._s_mask[i] = am
+        else:       # a smaller state: pad like pad_vertex_scores / pad_action_mask
+            vs = vs.reshape(-1, self.nf)
+            assert vs.shape[0] <= self.nhe and am.size == vs.shape[0] * self.apa, \
+                f"state with {vs.shape[0]} tokens / {am.size} actions does not fit a buffer of {self.nhe} x {self.apa}"
+            self._s_feat[i] = 0
+            self._s_feat[i, :vs.shape[0]] = vs
+            self._s_mask[i] = -np.inf
+            self._s_mask[i, :am.size] = am
         self._s_prob[i] = action_probability
         self._s_act[i] = action
         self._s_rew[i] = reward

@@ -469,3 +469,49 @@ def test_sample_actions_follow_the_distribution(ctx):
     assert np.all(np.abs(freq - p) <= 5 * sigma + 1e-9), np.max(np.abs(freq - p) / (sigma + 1e-12))
     assert np.all(freq[p == 0] == 0)
     pol.close()
+
+
+# ---- variable-size states: the reference pads (triangle_utilities.jl:31-55) ---------------------
+def test_variable_size_states_padded_like_the_reference(ctx):
+    """states with 3..8 tokens go into a buffer of 8: the update matches the oracle run on the reference's padding
+    (zeros / -Inf32 to the largest state), and padded actions get probability exactly 0"""
+    nf, nhe, apa, H, L = 8, 8, 4, 32, 2
+    rng = np.random.default_rng(21)
+    n = 96
+    states, feat, mask = [], np.zeros((n, nhe, nf), np.float32), np.full((n, nhe * apa), -np.inf, np.float32)
+    for i in range(n):
+        k = int(rng.integers(3, nhe + 1))
+        vs = rng.integers(-3, 9, (k, nf)).astype(np.float32)
+        am = np.where(rng.random(k * apa) < 0.2, -np.inf, 0.0).astype(np.float32)
+        am[0] = 0.0
+        states.append(P.StateData(vs, am))
+        feat[i, :k], mask[i, :k * apa] = vs, am
+    padded = P.prepare_state_data_for_batching_(list(states), nhe, apa)
+    np.testing.assert_array_equal(np.stack([s.vertex_score for s in padded]), feat)
+    np.testing.assert_array_equal(np.stack([s.action_mask for s in padded]), mask)
+    cfg = S.Config("ragged", 94, n, nf, nhe, apa, H, L, 32)
+    W, b = S.make_weights(cfg)
+    opol = O.Policy(nf, H, L, apa)
+    opol.W, opol.b = [w.copy() for w in W], [x.copy() for x in b]
+    probs = O.batch_action_probabilities(opol, feat, mask)
+    act = np.array([rng.choice(np.flatnonzero(np.isfinite(m))) + 1 for m in mask], np.int64)
+    old = probs[np.arange(n), act - 1].astype(np.float32)
+    rew = rng.integers(-4, 5, n).astype(np.float32)
+    term = (np.arange(n) % 12 == 11)
+    buf = P.DeviceRollouts(nf, nhe, apa, n, ctx)
+    for i in range(n):
+        P.update_(buf, states[i], old[i], act[i], rew[i], term[i])          # un-padded states
+    P.compute_state_value_(buf, 1.0)
+    pol = P.Policy(nf, H, L, apa, ctx, weights=W, biases=b)
+    dprobs = P.batch_action_probabilities(pol, P.StateData(feat, mask))
+    assert np.all(dprobs[~np.isfinite(mask)] == 0.0)
+    perm = np.random.default_rng(2).permutation(n) + 1
+    got = P.step_epoch_(pol, P.Adam(1e-4), P.construct_dataset(buf), 0.05, cfg.B, 0.01, perm=perm)
+    obuf = O.BufferRollouts(nf, nhe, apa)
+    obuf.update(feat, mask, old, act, O.compute_returns(rew, term, 1.0), term)
+    want = O.step_epoch(opol, O.Adam(1e-4), obuf, 0.05, cfg.B, 0.01, perm)
+    assert np.allclose(got, want, rtol=1e-5, atol=1e-7), (got, want)
+    Wd, bd = pol.weights()
+    for l in range(len(Wd)):
+        assert np.allclose(Wd[l], opol.W[l], rtol=1e-4, atol=2e-6)
+    pol.close(); buf.close()
