@@ -220,6 +220,7 @@ def _run_ours(args):
     gemm_mode = {"fp32": P.GEMM_FP32_SIMT, "tf32x3": P.GEMM_TF32X3_TC, "f16x3": P.GEMM_F16X3_TC}[args.gemm]
     pol = P.Policy(cfg.nf, cfg.H, cfg.L, cfg.apa, ctx, weights=W, biases=b)
     pol.set_gemm_mode(gemm_mode)
+    p2p = world > 1 and os.environ.get("PPO_B200_NO_P2P", "0") != "1" and D.enable_p2p_gradients(pol)
     opt = P.Optimiser(P.Adam(ETA))
     buf = P.DeviceRollouts(cfg.nf, cfg.nhe, cfg.apa, cfg.N, ctx)
     stream = torch.cuda.ExternalStream(ctx.stream())
@@ -364,6 +365,7 @@ def _run_ours(args):
                        "global_minibatch": B_local * world, "mlp": f"{cfg.L}x{cfg.H}", "nf": cfg.nf, "nhe": cfg.nhe,
                        "actions_per_state": cfg.A, "epochs_per_step": 1, "gemm_engine": args.gemm,
                        "parallelism": f"dp{world}" if world > 1 else "single",
+                       "grad_exchange": ("nvlink peer memory, fused into the Adam kernel" if p2p else "nccl all-reduce") if world > 1 else None,
                        "l2": "step inputs (4.6 GB) exceed L2; per-kernel timings flush L2 between launches (write 256 MB, then read 256 MB so that no dirty flush lines are written back inside the timed kernel)"},
             "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu, "e2e": e2e,
             "gpu_launches": launches, "clocks": clocks,

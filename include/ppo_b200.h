@@ -155,7 +155,14 @@ int ppo_policy_destroy(ppo_policy* p);
 int ppo_policy_read(ppo_policy* p, float* const* W, float* const* b);
 int ppo_policy_write(ppo_policy* p, const float* const* W, const float* const* b);
 int ppo_policy_set_gemm_mode(ppo_policy* p, int mode);
-int ppo_policy_get_gemm_mode(ppo_policy* p);   /* the engine in use (after PPO_GEMM_AUTO: the one that was picked) */
+int ppo_policy_get_gemm_mode(ppo_policy* p);
+/* Data parallelism over NVLink peer memory (one process per GPU, one node): instead of an NCCL all-reduce per minibatch the
+   Adam kernel reads every rank's published gradient through CUDA-IPC mappings and adds them in rank order (weights stay
+   bit-identical across ranks).  Every rank exports a 64-byte IPC handle, the handles are gathered by any transport
+   (rank-major, nranks x 64 bytes) and passed to connect.  Requires ppo_comm_init (rank / nranks); the per-epoch loss
+   history still goes through NCCL. */
+int ppo_policy_p2p_export(ppo_policy* p, void* handle64);
+int ppo_policy_p2p_connect(ppo_policy* p, int nranks, int rank, const void* handles);   /* the engine in use (after PPO_GEMM_AUTO: the one that was picked) */
 int64_t ppo_policy_num_params(ppo_policy* p);
 /* PPO.batch_action_probabilities(policy, state), test/quad_game_utilities.jl:73-79:
  * probs[nb][A] = softmax(reshape(policy(feat), :, nb) + mask). */

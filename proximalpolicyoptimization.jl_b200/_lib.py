@@ -60,6 +60,8 @@ SIGNATURES = {
     "ppo_policy_write": (c_int, [vp, PPF, PPF]),
     "ppo_policy_set_gemm_mode": (c_int, [vp, c_int]),
     "ppo_policy_get_gemm_mode": (c_int, [vp]),
+    "ppo_policy_p2p_export": (c_int, [vp, vp]),
+    "ppo_policy_p2p_connect": (c_int, [vp, c_int, c_int, vp]),
     "ppo_policy_num_params": (c_i64, [vp]),
     "ppo_batch_action_probabilities": (c_int, [vp, c_i64, c_int, PF, PF, PF]),
     "ppo_sample_actions": (c_int, [vp, c_i64, c_int, PF, PF, c_u64, PI64, PF, PF]),

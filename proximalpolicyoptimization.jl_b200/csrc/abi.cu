@@ -227,6 +227,12 @@ int step_core(ppo_policy* p, ppo_opt* opt, const ppo_batch& bt, int64_t nb, int 
                         inv_nb_global, p->dlogits, p->d_loss_partials, p->d_loss_hist + (d_step ? 0 : 2 * slot), nullptr,
                         d_step));
     PPO_TRY(policy_backward(p, bt.feat, M));
+    if (ctx->nccl_comm != nullptr && ctx->nranks > 1 && p2p_active(p)) {
+        // gradient all-reduce over NVLink peer memory, fused into the Adam kernel (dp_p2p.cu)
+        PPO_TRY(p2p_reduce_and_step(p, opt));
+        if (opt != nullptr) PPO_TRY(refresh_engine_weights(p));
+        return PPO_OK;
+    }
     if (ctx->nccl_comm != nullptr && ctx->nranks > 1) {
         // the fp16-split engine all-reduces every layer's gradient as soon as it is complete (overlapped with the rest of
         // the backward pass); the other engines reduce the whole flat vector here
@@ -752,6 +758,7 @@ int ppo_policy_destroy(ppo_policy* p) {
     free_workspace(p);
     tc_destroy(p);
     f16_destroy(p);
+    p2p_destroy(p);
     dev_free(p->params); dev_free(p->grads); dev_free(p->d_loss_partials); dev_free(p->d_loss_hist);
     free_batch(p->hbatch);
     delete p;
@@ -802,6 +809,19 @@ int ppo_policy_set_gemm_mode(ppo_policy* p, int mode) {
     else if (mode != PPO_GEMM_FP32_SIMT) PPO_TRY(tc_prepare(p, mode));
     p->gemm_mode = mode;
     return refresh_engine_weights(p);
+}
+
+int ppo_policy_p2p_export(ppo_policy* p, void* handle64) {
+    PPO_REQUIRE(p != nullptr && handle64 != nullptr, "p2p_export: null argument");
+    PPO_TRY(use(p->ctx));
+    return p2p_export(p, handle64);
+}
+int ppo_policy_p2p_connect(ppo_policy* p, int nranks, int rank, const void* handles) {
+    PPO_REQUIRE(p != nullptr && handles != nullptr, "p2p_connect: null argument");
+    PPO_TRY(use(p->ctx));
+    PPO_REQUIRE(p->ctx->nranks == nranks && p->ctx->rank == rank, "p2p_connect: communicator is rank %d of %d", p->ctx->rank,
+                p->ctx->nranks);
+    return p2p_connect(p, nranks, rank, handles);
 }
 
 int ppo_policy_get_gemm_mode(ppo_policy* p) { return p ? p->gemm_mode : PPO_ERR_INVALID; }
@@ -1098,6 +1118,7 @@ int ppo_step_epoch(ppo_policy* p, ppo_opt* opt, ppo_buf* buf, double epsilon, in
     }
     for (; k < nbatches; ++k) PPO_TRY(run_batch(k));
     if (dp) PPO_TRY(nccl_allreduce_f64(ctx, p->d_loss_hist, 2 * nbatches));
+    if (dp) PPO_TRY(p2p_check(p));
     PPO_TRY(d2h(ctx, ctx->h_pinned, p->d_loss_hist, (size_t)nbatches * 16));
     PPO_CUDA(cudaStreamSynchronize(ctx->stream));
     // Flux.mean(ppo_loss_history), Flux.mean(entropy_loss_history): unweighted by batch length, :127

@@ -8,7 +8,7 @@ FLAGS=(-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompil
        -Xptxas -v --expt-relaxed-constexpr)
 mkdir -p build
 pids=()
-for src in abi.cu scan.cu shuffle.cu gather.cu loss.cu gemm_simt.cu gemm_tc.cu gemm_f16.cu adam.cu bench_hooks.cu; do
+for src in abi.cu scan.cu shuffle.cu gather.cu loss.cu gemm_simt.cu gemm_tc.cu gemm_f16.cu adam.cu dp_p2p.cu bench_hooks.cu; do
   obj=build/${src%.cu}.o
   if [[ ! -f $obj || $src -nt $obj || common.cuh -nt $obj || gemm_tc.cuh -nt $obj || gemm_f16.cuh -nt $obj || tc_ptx.cuh -nt $obj || ../../include/ppo_b200.h -nt $obj ]]; then
     ( $NVCC "${FLAGS[@]}" -c "$src" -o "$obj" > "build/${src%.cu}.log" 2>&1 || { cat "build/${src%.cu}.log"; exit 1; } ) &

@@ -66,6 +66,7 @@ struct ppo_ctx {
     cudaStream_t comm_stream = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     bool comm_pending = false;
+    bool p2p_grads = false;          // a policy of this context exchanges gradients over peer memory (dp_p2p.cu)
     static constexpr int PINNED_DOUBLES = 1 << 16;
 };
 
@@ -129,6 +130,7 @@ struct ppo_policy {
     // tensor-core operand copies (tcgen05 modes), maintained by the Adam kernel / policy_write
     void* tc = nullptr;
     void* f16 = nullptr;              // fp16-split engine state (gemm_f16.cu)
+    void* dp = nullptr;               // peer-memory gradient exchange (dp_p2p.cu)
     // own minibatch staging for the host-array entry points
     ppo_batch hbatch;
 };
@@ -232,6 +234,14 @@ bool dp_overlap(ppo_ctx* ctx);
 int grads_ready(ppo_ctx* ctx, float* d_slice, int64_t n);
 int grads_join(ppo_ctx* ctx);
 int nccl_allreduce_f64(ppo_ctx* ctx, double* d_buf, int64_t n);
+
+// dp_p2p.cu: gradient all-reduce over NVLink peer memory fused into the Adam step (one process per GPU, CUDA IPC)
+bool p2p_active(const ppo_policy* p);
+int p2p_export(ppo_policy* p, void* handle64);
+int p2p_connect(ppo_policy* p, int nranks, int rank, const void* handles);
+int p2p_reduce_and_step(ppo_policy* p, ppo_opt* opt);
+int p2p_check(ppo_policy* p);
+void p2p_destroy(ppo_policy* p);
 
 // l2 flush helper
 int flush_l2(ppo_ctx* ctx);

@@ -116,7 +116,7 @@ int nccl_allreduce_f32_on(ppo_ctx* ctx, float* d_buf, int64_t n, cudaStream_t st
 
 bool dp_overlap(ppo_ctx* ctx) {
     static const int off = getenv("PPO_B200_NO_DP_OVERLAP") ? atoi(getenv("PPO_B200_NO_DP_OVERLAP")) : 0;
-    return ctx->nccl_comm != nullptr && ctx->nranks > 1 && !off;
+    return ctx->nccl_comm != nullptr && ctx->nranks > 1 && !off && !ctx->p2p_grads;
 }
 
 int grads_ready(ppo_ctx* ctx, float* d_slice, int64_t n) {

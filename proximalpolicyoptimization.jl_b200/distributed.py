@@ -45,6 +45,21 @@ def local_seed(seed, rank):
     return (int(seed) * 1000003 + int(rank)) & (2 ** 64 - 1)
 
 
+def enable_p2p_gradients(policy, backend_group=None):
+    """Exchange the minibatch gradient over NVLink peer memory, fused into the Adam kernel (csrc/dp_p2p.cu), instead of an
+    NCCL all-reduce per minibatch: every rank exports a CUDA-IPC handle of its exchange buffer, the handles are
+    all-gathered over torch.distributed, and every rank maps its peers' buffers.  Call after ``init_comm``, on every
+    rank, before the first update.  Returns False (and leaves the NCCL path in place) in a single-rank job."""
+    import torch.distributed as dist
+    rank, world = dist.get_rank(), dist.get_world_size()
+    if world == 1:
+        return False
+    handles = [None] * world
+    dist.all_gather_object(handles, policy.p2p_export(), group=backend_group)
+    policy.p2p_connect(world, rank, b"".join(handles))
+    return True
+
+
 def init_comm(ctx, backend_group=None):
     """Create the library's NCCL communicator across the ranks of torch.distributed: rank 0 draws
     the unique id, it is broadcast with the process group already initialised by the launcher."""

@@ -83,6 +83,15 @@ class Policy:
         _lib.check(_lib.load().ppo_policy_set_gemm_mode(self.handle, int(mode)))
         return self.gemm_mode
 
+    def p2p_export(self) -> bytes:
+        buf = C.create_string_buffer(64)
+        _lib.check(_lib.load().ppo_policy_p2p_export(self.handle, buf))
+        return buf.raw
+
+    def p2p_connect(self, nranks: int, rank: int, handles: bytes):
+        assert len(handles) == 64 * nranks
+        _lib.check(_lib.load().ppo_policy_p2p_connect(self.handle, int(nranks), int(rank), C.c_char_p(handles)))
+
     @property
     def gemm_mode(self) -> int:
         return int(_lib.load().ppo_policy_get_gemm_mode(self.handle))

@@ -12,7 +12,7 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, q, p2p=False):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     sys.path.insert(0, ROOT)
     import torch
@@ -38,6 +38,8 @@ def _worker(rank, world, port, q):
     buf = P.DeviceRollouts(cfg.nf, cfg.nhe, cfg.apa, n_use, ctx)
     buf.append(data["feat"][sl], data["mask"][sl], old[sl], data["action"][sl], ret, data["terminal"][sl])
     pol = P.Policy(cfg.nf, cfg.H, cfg.L, cfg.apa, ctx, weights=W, biases=b)
+    if p2p:
+        assert D.enable_p2p_gradients(pol)
     opt = P.Adam(1e-4)
     losses = P.step_epoch_(pol, opt, P.construct_dataset(buf), 0.05, 64, 0.01, seed=D.local_seed(99, rank))
     Wd, bd = pol.weights()
@@ -48,7 +50,9 @@ def _worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
-def test_two_rank_epoch_matches_sharded_oracle():
+@pytest.mark.parametrize("p2p", [False, True], ids=["nccl", "peer-memory"])
+def test_two_rank_epoch_matches_sharded_oracle(p2p):
+    """p2p = True: the gradient exchange over CUDA-IPC peer memory fused into Adam (csrc/dp_p2p.cu) instead of NCCL"""
     import torch
     if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
@@ -61,7 +65,7 @@ def test_two_rank_epoch_matches_sharded_oracle():
     mctx = mp.get_context("spawn")
     q = mctx.Queue()
     port = 29600 + (os.getpid() % 1000)
-    procs = [mctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    procs = [mctx.Process(target=_worker, args=(r, world, port + (7 if p2p else 0), q, p2p)) for r in range(world)]
     [p.start() for p in procs]
     res = {}
     for _ in range(world):
