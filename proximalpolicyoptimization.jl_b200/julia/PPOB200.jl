@@ -185,6 +185,16 @@ function batch_sample_actions(p::DevicePolicy, vertex_score::Array{Float32,3}, a
     return actions, probs
 end
 
+# Data parallelism over NVLink peer memory (one Julia process per GPU): `handles = allgather(p2p_export(p))` with any
+# transport (MPI.jl, Distributed, files), then `p2p_connect!(p, nranks, rank, handles)` on every rank.
+function p2p_export(p::DevicePolicy)
+    h = Vector{UInt8}(undef, 64)
+    check(ccall((:ppo_policy_p2p_export, lib), Cint, (Ptr{Cvoid}, Ptr{UInt8}), p.h, h))
+    return h
+end
+p2p_connect!(p::DevicePolicy, nranks::Integer, rank::Integer, handles::Vector{Vector{UInt8}}) =
+    check(ccall((:ppo_policy_p2p_connect, lib), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{UInt8}), p.h, nranks, rank, reduce(vcat, handles)))
+
 mutable struct DeviceAdam
     h::Ptr{Cvoid}
     eta::Float64
