@@ -12,7 +12,8 @@ max over ranks) with the buffer resident in HBM; `e2e` = the same through the pu
 (pinned) buffers: the H2D append of the whole buffer and the D2H read of the losses are inside the
 timed region.  N=1 workload: config C3 (1M transitions, MLP 3x512, B=65536).  N>1: every rank holds
 a C3-sized shard (weak scaling; at N=8 this is C4: 8M transitions, global B=65536, B/N rows per
-rank) and gradients are all-reduced per minibatch.
+rank) and the minibatch gradients are summed over the ranks inside the Adam kernel through NVLink
+peer memory (CUDA IPC; PPO_B200_NO_P2P=1 selects the NCCL all-reduce instead).
 
 --impl reference times the CPU restatement of the reference (oracle/: Julia is not installable in
 this image) on a bounded sample of the same workload with all host threads.

@@ -18,12 +18,14 @@
 // Scales are exact powers of two, so scaling/unscaling introduces no rounding.
 //
 // Kernels (all sm_100a, hand-written):
-//   f16_gemm_kk_kernel  forward / dgrad: persistent, warp-specialised (TMA warp, one MMA thread, 8 epilogue
-//                       warps), UMMA 128 x BN x 16, 64-element k-blocks (128-byte swizzle rows), contraction
-//                       cut into 128-element chains folded into fp32 registers with round-to-nearest adds
-//                       (the tensor core accumulates with round-toward-zero), epilogue = unscale + bias +
-//                       leakyrelu (or leakyrelu' gate + bias-gradient column sums), rescale, fp16 split,
-//                       swizzled staging, TMA store.
+//   f16_gemm_kk_kernel  forward / dgrad: persistent, warp-specialised (TMA warp, one MMA thread, 16 epilogue
+//                       warps), 64-element k-blocks (128-byte swizzle rows), contraction cut into 256-element
+//                       chains that the epilogue warps fold into fp32 registers (the tensor core accumulates
+//                       with round-toward-zero; the fold compensates the resulting deficit), epilogue = unscale
+//                       + bias + leakyrelu + sign bits (or sign-bit gate + bias-gradient column sums), rescale,
+//                       packed fp16 split, per-warp swizzled staging, per-warp TMA stores.  K > 128: CTA PAIRS
+//                       (2-CTA clusters, tcgen05.mma.cta_group::2, UMMA 256 x 256 x 16, each CTA stages half of
+//                       the weight tile); K <= 128: 128 x 128 tiles with 4 TMEM stages (epilogue-bound shapes).
 //   f16_gemm_mn_kernel  wgrad: both operands MN-major straight from the row-major activations (3-D tensor
 //                       maps produce the canonical MN-major SWIZZLE_128B atoms), split over rows, fixed-order
 //                       reduction (deterministic).
