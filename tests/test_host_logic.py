@@ -103,3 +103,35 @@ def test_gloo_world2_sharding_roundtrip():
     (a0, b0, s0, _), (a1, b1, s1, _) = res[0]
     assert a0 == 0 and b0 == a1 and b1 == cfg.N
     assert abs((s0 + s1) - float(whole.sum())) < 1e-3
+
+
+def test_padding_hooks_like_the_reference():
+    """pad_vertex_scores / pad_action_mask / prepare_state_data_for_batching! of
+    examples/triangle/distance_weighted/triangle_utilities.jl:31-55: zero columns, -Inf32 actions, to the largest state"""
+    import ppo_b200 as P
+    states = [P.StateData(np.ones((3, 2), np.float32), np.zeros(6, np.float32)),
+              P.StateData(2 * np.ones((5, 2), np.float32), np.zeros(10, np.float32))]
+    P.prepare_state_data_for_batching_(states)
+    assert [s.vertex_score.shape for s in states] == [(5, 2), (5, 2)]
+    assert np.all(states[0].vertex_score[3:] == 0) and np.all(states[0].vertex_score[:3] == 1)
+    assert np.all(np.isneginf(states[0].action_mask[6:])) and np.all(states[0].action_mask[:6] == 0)
+    assert states[0].action_mask.dtype == np.float32
+    batched = P.batch_state(states)
+    assert batched.vertex_score.shape == (2, 5, 2) and batched.action_mask.shape == (2, 10)
+    # padding to a fixed buffer capacity (what DeviceRollouts.update_ does)
+    vs = P.pad_vertex_scores([np.ones((3, 2))], 8)
+    am = P.pad_action_mask([np.zeros(12)], 32)
+    assert vs[0].shape == (8, 2) and am[0].shape == (32,) and np.isneginf(am[0][12:]).all()
+
+
+def test_p2p_gradient_exchange_is_a_noop_for_one_rank():
+    """enable_p2p_gradients leaves the NCCL path in place in a single-rank job (no GPU needed)"""
+    import torch.distributed as dist
+    from ppo_b200 import distributed as D
+    import tempfile
+    with tempfile.NamedTemporaryFile() as f:
+        dist.init_process_group("gloo", init_method=f"file://{f.name}", rank=0, world_size=1)
+        try:
+            assert D.enable_p2p_gradients(policy=None) is False
+        finally:
+            dist.destroy_process_group()
