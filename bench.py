@@ -118,9 +118,22 @@ def cpu_reference_step(cfg, data, W, b, rows, threads):
     return t_scan * rows / n + t_batch
 
 
+def host_blas_threads(want_all=False):
+    """The numpy BLAS pool does the CPU arm's GEMMs.  torchrun exports OMP_NUM_THREADS=1, so the reference arm asks
+    for every core this process may run on; returns (context manager or None, threads in use)."""
+    try:
+        from threadpoolctl import threadpool_info, threadpool_limits
+    except Exception:        # threadpoolctl missing: report what the environment says
+        return None, int(os.environ.get("OMP_NUM_THREADS", os.cpu_count() or 1))
+    ncpu = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    if want_all:
+        return threadpool_limits(limits=ncpu), ncpu
+    info = [d.get("num_threads", 1) for d in threadpool_info() if d.get("user_api") in ("blas", "openmp")]
+    return None, (max(info) if info else 1)
+
+
 def cpu_baseline(cfg, data, W, b, target_s=12.0):
-    import torch
-    threads = torch.get_num_threads()
+    _, threads = host_blas_threads()
     rows = min(2048, cfg.B)
     t = cpu_reference_step(cfg, data, W, b, rows, threads)
     rate = rows / t
@@ -395,7 +408,8 @@ def run_reference(args):
     data = S.make_buffer(small)
     W, b = S.make_weights(cfg)
     data["old"] = np.full(n, 1.0 / cfg.A, np.float32)
-    threads = torch.get_num_threads()
+    limiter, threads = host_blas_threads(want_all=True)      # all host cores, also under torchrun (OMP_NUM_THREADS=1)
+    torch.set_num_threads(threads)
     rows = min(cfg.B, 2048)
     t = cpu_reference_step(cfg, data, W, b, rows, threads)
     rows = int(min(cfg.B, n, max(rows, rows / t * 8.0)))   # ~8 s of CPU work per step
