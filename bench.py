@@ -353,7 +353,7 @@ def _run_ours(args):
         passes = 3 if args.gemm in ("tf32x3", "f16x3") else 1
         # ceiling of the 3-pass split: tf32 runs at half the bf16/fp16 rate (peak / 6); fp16 at the full rate (peak / 3)
         ceiling = pk["bf16_sustained"] / (6.0 if args.gemm == "tf32x3" else 3.0)
-        kname = {"tf32x3": "tc_gemm_kk_kernel<256>", "f16x3": "f16_gemm_kk_kernel<256>", "fp32": "sgemm_kernel"}[args.gemm]
+        kname = {"tf32x3": "tc_gemm_kk_kernel<256>", "f16x3": "f16_gemm_kk_kernel<256, CTA pair>", "fp32": "sgemm_kernel"}[args.gemm]
         roofline = {"bound": "tensor", "achieved": ach, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
                     "frac": round(ach / pk["bf16_sustained"], 4),
                     "traffic": ({"tf32x3": 8.65e9, "f16x3": 4.34e9}.get(args.gemm)
