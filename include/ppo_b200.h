@@ -154,15 +154,25 @@ int ppo_policy_create(ppo_ctx* ctx, int n_layers, const int* dims, const float* 
 int ppo_policy_destroy(ppo_policy* p);
 int ppo_policy_read(ppo_policy* p, float* const* W, float* const* b);
 int ppo_policy_write(ppo_policy* p, const float* const* W, const float* const* b);
+/* a new policy runs on PPO_GEMM_AUTO; set_gemm_mode selects another engine (or fails loudly, PPO_ERR_INVALID, when the
+ * policy's shapes are outside that engine's contract) */
 int ppo_policy_set_gemm_mode(ppo_policy* p, int mode);
+/* the engine in use (after PPO_GEMM_AUTO: the one that was picked) */
 int ppo_policy_get_gemm_mode(ppo_policy* p);
+/* Parity instrumentation: the leakyrelu' branch (1 = pre-activation > 0, 0 = slope branch) that the backward pass of
+ * the LAST minibatch applies to every element of hidden activation `layer` (1 .. n_layers-1, the output of Dense
+ * `layer`), gates_out[rows][dims[layer]], rows = tokens of that minibatch.  leakyrelu' is discontinuous at 0
+ * (ASSUMED NNlib.leakyrelu, test/policy.jl:11-15), so a gradient comparison against another evaluation is only
+ * meaningful when both sides take the same branch for pre-activations within rounding of zero; the tests feed these
+ * gates to the fp64 oracle and check separately that every disagreement sits at a ~0 pre-activation. */
+int ppo_policy_read_gates(ppo_policy* p, int layer, int64_t rows, uint8_t* gates_out);
 /* Data parallelism over NVLink peer memory (one process per GPU, one node): instead of an NCCL all-reduce per minibatch the
    Adam kernel reads every rank's published gradient through CUDA-IPC mappings and adds them in rank order (weights stay
    bit-identical across ranks).  Every rank exports a 64-byte IPC handle, the handles are gathered by any transport
    (rank-major, nranks x 64 bytes) and passed to connect.  Requires ppo_comm_init (rank / nranks); the per-epoch loss
    history still goes through NCCL. */
 int ppo_policy_p2p_export(ppo_policy* p, void* handle64);
-int ppo_policy_p2p_connect(ppo_policy* p, int nranks, int rank, const void* handles);   /* the engine in use (after PPO_GEMM_AUTO: the one that was picked) */
+int ppo_policy_p2p_connect(ppo_policy* p, int nranks, int rank, const void* handles);
 int64_t ppo_policy_num_params(ppo_policy* p);
 /* PPO.batch_action_probabilities(policy, state), test/quad_game_utilities.jl:73-79:
  * probs[nb][A] = softmax(reshape(policy(feat), :, nb) + mask). */

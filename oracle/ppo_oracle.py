@@ -373,7 +373,8 @@ def ppo_loss_with_entropy(policy, feat, mask, actions1, old_probs, advantage, ep
     return ppoloss, entropyloss
 
 
-def loss_grad_logits(logits, mask, actions1, old_probs, advantage, epsilon, entropy_weight, smooth=F32(1e-8)):
+def loss_grad_logits(logits, mask, actions1, old_probs, advantage, epsilon, entropy_weight, smooth=F32(1e-8),
+                     nb_total=None):
     """Analytic d(ppoloss + entropy_weight*entropyloss)/dlogits — what Zygote differentiates at
     src/train.jl:67-79 restricted to the part after the MLP.  Returns
     (ppoloss, entropyloss_unweighted, probs, dlogits[nb, A]).
@@ -383,34 +384,47 @@ def loss_grad_logits(logits, mask, actions1, old_probs, advantage, epsilon, entr
 
     ASSUMPTION: on a tie gain == clip the derivative follows ``gain`` (Base.min returns its
     first argument on ties; measure-zero in practice).
+
+    ``nb_total``: the rows are a chunk of a minibatch of nb_total samples (test helper for minibatches too large to
+    hold in Float64 at once): the 1/nb factors of the gradient use nb_total, the returned losses are the chunk's means.
     """
     dt = logits.dtype.type
     nb, A = logits.shape
+    nbt = nb if nb_total is None else int(nb_total)
     z = logits + mask
     p = softmax_cols(z)
     ppoloss, entropyloss, sel, gain, clip = ppo_loss_terms(p, actions1, old_probs, advantage, epsilon)
     sp = dt(dt(1.0) - dt(smooth)) * p + dt(dt(smooth) / dt(A))
     w = dt(entropy_weight)
-    g = (w / dt(nb)) * dt(dt(1.0) - dt(smooth)) * (np.log(sp) + dt(1.0))
+    g = (w / dt(nbt)) * dt(dt(1.0) - dt(smooth)) * (np.log(sp) + dt(1.0))
     active = gain.astype(F64) <= clip
-    coef = np.where(active, advantage / old_probs / dt(nb), dt(0)).astype(logits.dtype)
+    coef = np.where(active, advantage / old_probs / dt(nbt), dt(0)).astype(logits.dtype)
     g[np.arange(nb), np.asarray(actions1, dtype=np.int64) - 1] -= coef
     dz = p * (g - (p * g).sum(axis=-1, keepdims=True))
     return ppoloss, entropyloss, p, dz
 
 
-def policy_gradient(policy: Policy, feat, mask, actions1, old_probs, advantage, epsilon, entropy_weight):
+def policy_gradient(policy: Policy, feat, mask, actions1, old_probs, advantage, epsilon, entropy_weight,
+                    gates=None, nb_total=None, return_acts=False):
     """Gradient of ``ppoloss + entropyloss*entropy_weight`` w.r.t. ``Flux.params(policy)`` —
     src/train.jl:65-79 — by the Dense pullbacks (dW = x' * delta, db = sum delta, dx = delta * W').
     ASSUMPTION: leakyrelu'(z) = 1 for z > 0 else a (also at z == 0).
-    Returns (ppoloss, entropyloss*entropy_weight, dW list, db list)."""
+    Returns (ppoloss, entropyloss*entropy_weight, dW list, db list[, acts]).
+
+    ``gates`` (test instrumentation, no reference counterpart): ``gates[l]`` (l = 1..L-1, boolean [tokens, dims[l]])
+    replaces this evaluation's own ``acts[l] > 0`` as the leakyrelu' branch of hidden activation l.  leakyrelu' is
+    discontinuous at 0, so two evaluations that round differently can take different branches for a pre-activation
+    within rounding of zero; handing the device's branches (ppo_policy_read_gates) to the oracle makes the gradient
+    comparison well posed, and the tests check separately that every disagreement sits at such a pre-activation.
+    ``nb_total``: see :func:`loss_grad_logits`."""
     nb = feat.shape[0]
     dt = policy.W[0].dtype
     x = feat.reshape(-1, feat.shape[-1]).astype(dt)        # tokens [nb*nhe, nf]
     logits_tok, acts = mlp_forward(policy, x, keep=True)
     logits = logits_tok.reshape(nb, -1)
     ppoloss, entropyloss, _, dz = loss_grad_logits(
-        logits, mask.astype(dt), actions1, old_probs.astype(dt), advantage.astype(dt), epsilon, entropy_weight)
+        logits, mask.astype(dt), actions1, old_probs.astype(dt), advantage.astype(dt), epsilon, entropy_weight,
+        nb_total=nb_total)
     delta = dz.reshape(logits_tok.shape).astype(dt)
     L = len(policy.W)
     dW, db = [None] * L, [None] * L
@@ -419,9 +433,10 @@ def policy_gradient(policy: Policy, feat, mask, actions1, old_probs, advantage, 
         db[l] = delta.sum(axis=0)
         if l > 0:
             dx = delta @ policy.W[l].T
-            h = acts[l]
-            delta = np.where(h > 0, dx, dt.type(getattr(policy, "slope", LEAKY_SLOPE)) * dx)
-    return ppoloss, F64(entropyloss) * F64(entropy_weight), dW, db
+            pos = (acts[l] > 0) if gates is None else np.asarray(gates[l]).astype(bool)
+            delta = np.where(pos, dx, dt.type(getattr(policy, "slope", LEAKY_SLOPE)) * dx)
+    out = (ppoloss, F64(entropyloss) * F64(entropy_weight), dW, db)
+    return out + (acts,) if return_acts else out
 
 
 # --------------------------------------------------------------------------------------

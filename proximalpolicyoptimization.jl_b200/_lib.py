@@ -60,6 +60,7 @@ SIGNATURES = {
     "ppo_policy_write": (c_int, [vp, PPF, PPF]),
     "ppo_policy_set_gemm_mode": (c_int, [vp, c_int]),
     "ppo_policy_get_gemm_mode": (c_int, [vp]),
+    "ppo_policy_read_gates": (c_int, [vp, c_int, c_i64, PU8]),
     "ppo_policy_p2p_export": (c_int, [vp, vp]),
     "ppo_policy_p2p_connect": (c_int, [vp, c_int, c_int, vp]),
     "ppo_policy_num_params": (c_i64, [vp]),

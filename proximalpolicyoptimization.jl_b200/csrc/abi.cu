@@ -315,6 +315,13 @@ int append_common(ppo_buf* buf, int64_t n, const void* feat, bool feat_i64, cons
 }  // namespace
 
 namespace {
+// leakyrelu' gate of an fp32 activation (FFMA and tf32 engines gate on `act > 0`)
+__global__ void __launch_bounds__(256)
+gates_from_f32_kernel(const float* __restrict__ act, int64_t n, uint8_t* __restrict__ out) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = act[i] > 0.0f ? 1 : 0;
+}
+
 __global__ void __launch_bounds__(256)
 l2_read_sweep_kernel(const uint4* __restrict__ p, size_t n16, unsigned* sink) {
     unsigned acc = 0u;
@@ -730,8 +737,9 @@ int ppo_policy_create(ppo_ctx* ctx, int n_layers, const int* dims, const float* 
     p->dims.assign(dims, dims + n_layers + 1);
     int64_t off = 0;
     for (int l = 0; l < n_layers; ++l) {
+        // Flux.params order, densely packed (no padding): kernels that use vector loads check the alignment of a
+        // segment at run time and fall back to scalar accesses
         p->w_off.push_back(off); off += (int64_t)dims[l] * dims[l + 1];
-        // keep every segment 16-byte aligned for the vector loads
         p->b_off.push_back(off); off += dims[l + 1];
     }
     p->P = off;
@@ -747,6 +755,9 @@ int ppo_policy_create(ppo_ctx* ctx, int n_layers, const int* dims, const float* 
     } else {
         PPO_CUDA(cudaMemsetAsync(p->params, 0, (size_t)p->P * 4, ctx->stream));
     }
+    // default engine: the fastest one whose shape contract the policy meets (every binding sees the same default)
+    s = ppo_policy_set_gemm_mode(p, PPO_GEMM_AUTO);
+    if (s != PPO_OK) { ppo_policy_destroy(p); return s; }
     *out = p;
     return PPO_OK;
 }
@@ -825,6 +836,29 @@ int ppo_policy_p2p_connect(ppo_policy* p, int nranks, int rank, const void* hand
 }
 
 int ppo_policy_get_gemm_mode(ppo_policy* p) { return p ? p->gemm_mode : PPO_ERR_INVALID; }
+
+int ppo_policy_read_gates(ppo_policy* p, int layer, int64_t rows, uint8_t* gates_out) {
+    PPO_REQUIRE(p != nullptr && gates_out != nullptr, "read_gates: null argument");
+    ppo_ctx* ctx = p->ctx;
+    PPO_TRY(use(ctx));
+    PPO_REQUIRE(layer >= 1 && layer <= p->L - 1, "read_gates: hidden layer %d of %d", layer, p->L - 1);
+    PPO_REQUIRE(rows >= 1 && rows <= p->ws_tokens, "read_gates: %lld rows, the last pass held %lld", (long long)rows,
+                (long long)p->ws_tokens);
+    const int64_t n = rows * p->dims[layer];
+    PPO_TRY(ensure_scratch(ctx, (size_t)n));
+    uint8_t* d_out = (uint8_t*)ctx->d_scratch;
+    if (p->gemm_mode == PPO_GEMM_F16X3_TC) {
+        PPO_TRY(f16_read_gates(p, layer, rows, d_out));
+    } else {
+        const unsigned blocks = (unsigned)std::min<int64_t>(ceil_div(n, 256), (int64_t)ctx->num_sms * 16);
+        gates_from_f32_kernel<<<blocks, 256, 0, ctx->stream>>>(p->act[layer], n, d_out);
+        ctx->launches += 1;
+        PPO_CUDA(cudaGetLastError());
+    }
+    PPO_TRY(d2h(ctx, gates_out, d_out, (size_t)n));
+    PPO_CUDA(cudaStreamSynchronize(ctx->stream));
+    return PPO_OK;
+}
 
 int64_t ppo_policy_num_params(ppo_policy* p) { return p ? p->P : -1; }
 

@@ -13,7 +13,6 @@
 #include "gemm_f16.cuh"
 
 namespace ppo {
-extern int g_scan_dbg;
 namespace {
 
 __device__ __forceinline__ uint32_t hash32(uint64_t x) {
@@ -123,11 +122,8 @@ extern "C" int ppo_bench_kernel(ppo_ctx* ctx, const char* which, int64_t n, int 
         PPO_TRY(fill(ctx, r, n, 1, 1, 11));
         fill_terminal_kernel<<<148 * 8, 256, 0, ctx->stream>>>(t, n, a > 0 ? a : 15, 12);
         const double disc = (b == 0) ? 1.0 : 0.99;
-        g_scan_dbg = c;   // timing experiments only (1: skip look-back, 4: skip stats, 8: no look-ahead)
-        int st = time_loop(ctx, sc, iters, flush_l2_flag,
-                           [&]() { return launch_returns_scan(ctx, r, o, t, n, disc, 0, w == "scan_norm" ? stats : nullptr, scratch); }, ms_out);
-        g_scan_dbg = 0;
-        PPO_TRY(st);
+        PPO_TRY(time_loop(ctx, sc, iters, flush_l2_flag,
+                          [&]() { return launch_returns_scan(ctx, r, o, t, n, disc, 0, w == "scan_norm" ? stats : nullptr, scratch); }, ms_out));
         *work_out = 9.0 * (double)n;
         return PPO_OK;
     }

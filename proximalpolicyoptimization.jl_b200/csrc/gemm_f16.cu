@@ -64,7 +64,15 @@ constexpr int F_THREADS = 64 + F_EPI_THREADS;
 constexpr int F_KK_EPI_THREADS = 512;       // kk kernel: 16 epilogue warps = 4 lane quarters x 4 column quarters (the
 constexpr int F_KK_THREADS = 64 + F_KK_EPI_THREADS;   // per-element epilogue is issue/latency bound: more warps, fewer columns each)
 constexpr int FA_TILE_BYTES = F_BM * F_BK * 2;   // 16 KB
-constexpr int F_MAX_LAYERS = 8;
+constexpr int F_MAX_LAYERS = 8;              // table size
+// Depth contract.  A tensor's exponent comes from an a-priori bound (plan_fwd / plan_bwd) that runs ahead of the real
+// abs-max by ~0.87 sqrt(K) per layer (2^4.3 at K = 512, 2^4.8 at K = 1024: max column L1 norm of a Glorot matrix against
+// the ~unit gain of the layer).  A scaled element keeps an absolute error <= 2^-25 even when the looseness pushes it into
+// fp16's subnormal range, i.e. <= looseness * 2^-39 of the tensor's max; 1e-5 = 2^-16.6 therefore allows a total
+// looseness of 2^22: four hidden layers of width <= 1024 (4 x 4.8 = 19.2 bits) are inside, deeper policies are refused
+// (PPO_GEMM_AUTO then picks the tf32 engine, whose fp32-range operands need no scaling).
+constexpr int F_MAX_HIDDEN = 4;
+constexpr int F_MAX_WIDTH = 1024;
 constexpr int F_EXP_TARGET = 14;            // bound * 2^e <= 2^14 (fp16 max is ~2^16)
 constexpr int F_EXP_CLAMP = 60;
 
@@ -756,6 +764,24 @@ signbits_kernel(const float* __restrict__ x, int64_t M, int N, uint32_t* __restr
     }
 }
 
+// the leakyrelu' gates the backward pass uses, unpacked to one byte per activation (parity tests compare them with the
+// oracle's own pre-activation signs): from the sign-bit words of a hidden activation ...
+__global__ void __launch_bounds__(256)
+gates_from_signbits_kernel(const uint32_t* __restrict__ signs, int64_t M, int N, uint8_t* __restrict__ out) {
+    const int nw = N >> 5;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < M * N; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t row = i / N;
+        const int col = (int)(i % N);
+        out[i] = (uint8_t)((signs[sign_index(row, col >> 5, nw)] >> (col & 31)) & 1u);
+    }
+}
+// ... or, for the last hidden activation, from sign(hi) exactly as head_bwd16_kernel gates
+__global__ void __launch_bounds__(256)
+gates_from_hi_kernel(const __half* __restrict__ hi, int64_t n, uint8_t* __restrict__ out) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = __half2float(hi[i]) > 0.0f ? 1 : 0;
+}
+
 // W[K][N] * scale -> hi/lo of W and of W^T[N][K]
 __global__ void __launch_bounds__(256)
 weight_prep16_kernel(const float* __restrict__ W, __half* __restrict__ W_hi, __half* __restrict__ W_lo,
@@ -1345,10 +1371,12 @@ int ensure_f16_workspace(ppo_policy* p, int64_t tokens) {
 int f16_prepare(ppo_policy* p) {
     PPO_TRY(load_encode16());
     const int L = p->L;
-    PPO_REQUIRE(L >= 2 && L <= F_MAX_LAYERS, "fp16-split engine: needs 2..%d Dense layers (have %d); use PPO_GEMM_FP32_SIMT",
-                F_MAX_LAYERS, L);
+    static_assert(F_MAX_HIDDEN + 1 <= F_MAX_LAYERS, "layer table too small");
+    PPO_REQUIRE(L >= 2 && L - 1 <= F_MAX_HIDDEN, "fp16-split engine: needs 1..%d hidden layers (have %d): the a-priori scale "
+                "bounds lose 1e-5 parity beyond that depth; use PPO_GEMM_TF32X3_TC or PPO_GEMM_FP32_SIMT", F_MAX_HIDDEN, L - 1);
     for (int l = 0; l + 1 < L; ++l) {
         const int K = p->dims[l], N = p->dims[l + 1];
+        PPO_REQUIRE(N <= F_MAX_WIDTH, "fp16-split engine: hidden width %d > %d", N, F_MAX_WIDTH);
         PPO_REQUIRE(K % 8 == 0 && N % 32 == 0 && (l == 0 || K % 32 == 0),
                     "fp16-split engine: layer %d (%d -> %d) needs in %% 8 == 0 and hidden widths %% 32 == 0; "
                     "use PPO_GEMM_FP32_SIMT for this policy", l, K, N);
@@ -1469,6 +1497,21 @@ int f16_backward(ppo_policy* p, int64_t M) {
             pp ^= 1;
         }
     }
+    return PPO_OK;
+}
+
+// gates of hidden activation l (1..L-1) of the last forward pass -> d_out[M][dims[l]] (1 = positive branch)
+int f16_read_gates(ppo_policy* p, int l, int64_t M, uint8_t* d_out) {
+    F16State* st = state(p);
+    PPO_REQUIRE(st != nullptr && M <= st->tokens, "fp16-split engine: no forward pass of %lld tokens to read gates from", (long long)M);
+    ppo_ctx* ctx = p->ctx;
+    const int N = p->dims[l];
+    const int64_t n = M * N;
+    const unsigned blocks = (unsigned)std::min<int64_t>(ceil_div(n, 256), (int64_t)ctx->num_sms * 16);
+    if (l < p->L - 1) gates_from_signbits_kernel<<<blocks, 256, 0, ctx->stream>>>(st->act_sign[l], M, N, d_out);
+    else gates_from_hi_kernel<<<blocks, 256, 0, ctx->stream>>>(st->act_hi[l], n, d_out);
+    ctx->launches += 1;
+    PPO_CUDA(cudaGetLastError());
     return PPO_OK;
 }
 

@@ -14,6 +14,8 @@ int f16_refresh_weights(ppo_policy* p);
 int f16_forward(ppo_policy* p, const float* X, int64_t M);
 // whole-MLP backward from p->dlogits -> p->grads
 int f16_backward(ppo_policy* p, int64_t M);
+// the leakyrelu' gates of hidden activation l (1..L-1) as the backward pass of the last minibatch applies them
+int f16_read_gates(ppo_policy* p, int l, int64_t M, uint8_t* d_out);
 void f16_destroy(ppo_policy* p);
 
 // ---- stand-alone entry points on device pointers (ppo_dense_op / ppo_bench_kernel) ----

@@ -100,16 +100,12 @@ int nccl_destroy(ppo_ctx* ctx) {
 
 int nccl_allreduce_f32(ppo_ctx* ctx, float* d_buf, int64_t n) {
     PPO_REQUIRE(ctx->nccl_comm != nullptr, "no communicator");
-    static const int skip = getenv("PPO_B200_SKIP_ALLREDUCE") ? atoi(getenv("PPO_B200_SKIP_ALLREDUCE")) : 0;
-    if (skip) return PPO_OK;
     PPO_NCCL(g_api.AllReduce(d_buf, d_buf, (size_t)n, ncclFloat32, ncclSum, (ncclComm_t)ctx->nccl_comm, ctx->stream));
     return PPO_OK;
 }
 
 int nccl_allreduce_f32_on(ppo_ctx* ctx, float* d_buf, int64_t n, cudaStream_t stream) {
     PPO_REQUIRE(ctx->nccl_comm != nullptr, "no communicator");
-    static const int skip = getenv("PPO_B200_SKIP_ALLREDUCE") ? atoi(getenv("PPO_B200_SKIP_ALLREDUCE")) : 0;
-    if (skip) return PPO_OK;      // timing experiments only (scripts/dp8_matrix.sh): the result is then wrong
     PPO_NCCL(g_api.AllReduce(d_buf, d_buf, (size_t)n, ncclFloat32, ncclSum, (ncclComm_t)ctx->nccl_comm, stream));
     return PPO_OK;
 }

@@ -68,6 +68,44 @@ __host__ __device__ inline ScanScratch carve(void* scratch, int64_t tiles) {
     return s;
 }
 
+// Decoupled look-back of tile t over the tiles to its right (ids t-1, t-2, ...), executed by one whole warp: lane l
+// inspects tile base - l, so one round covers 32 predecessors.  The round ends at the nearest tile with a published
+// inclusive value (lane k): carry = (agg_0 o ... o agg_{k-1})(incl_k); without one the 32 aggregates are composed and the
+// window moves 32 tiles further.  It runs only inside episodes longer than a tile plus the look-ahead window.
+__device__ __forceinline__ double warp_lookback(const ScanScratch sc, int t, int lane) {
+    Map cur{1.0, 0.0};
+    int base = t - 1;
+    for (;;) {
+        const int j = base - lane;
+        int f;
+        unsigned term;
+        for (;;) {
+            f = j >= 0 ? ld_acquire_i32(sc.flags + j) : 2;     // (tile 0 always publishes an inclusive value)
+            term = __ballot_sync(0xffffffffu, f == 2);
+            const unsigned need = term ? ((1u << (__ffs(term) - 1)) - 1u) : 0xffffffffu;   // lanes nearer than the terminator
+            const unsigned pending = __ballot_sync(0xffffffffu, f == 0) & need;
+            if (!pending) break;
+            __nanosleep(20);
+        }
+        const int k = term ? (__ffs(term) - 1) : 32;
+        Map m{1.0, 0.0};
+        if (lane < k) { m.A = __ldcg(sc.aggA + j); m.B = __ldcg(sc.aggB + j); }
+        else if (lane == k) { m.A = 0.0; m.B = j >= 0 ? __ldcg(sc.incl + j) : 0.0; }
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            Map o;
+            o.A = __shfl_down_sync(0xffffffffu, m.A, d);
+            o.B = __shfl_down_sync(0xffffffffu, m.B, d);
+            if (lane + d < 32) m = compose(m, o);
+        }
+        m.A = __shfl_sync(0xffffffffu, m.A, 0);
+        m.B = __shfl_sync(0xffffffffu, m.B, 0);
+        cur = compose(cur, m);
+        if (cur.A == 0.0) return cur.B;      // reached an inclusive value (or an episode end)
+        base -= 32;
+    }
+}
+
 constexpr int SCAN_LOOK = 128;   // transitions right of the tile inspected for an episode end (4 per lane of warp 0)
 
 // one pipeline stage in shared memory: the tile's rewards in the padded blocked arrangement, its terminals, and
@@ -102,7 +140,7 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 template <bool F32CARRY, bool G1>
 __global__ void __launch_bounds__(SCAN_THREADS, 4)
 returns_scan_kernel(const float* __restrict__ rew, float* __restrict__ out, const uint8_t* __restrict__ term, int64_t n,
-                    double g, double g8, int tiles, ScanScratch sc, double* __restrict__ tile_stats, int dbg) {
+                    double g, double g8, int tiles, ScanScratch sc, double* __restrict__ tile_stats) {
     extern __shared__ __align__(16) unsigned char scan_smem[];
     ScanStage* stages = reinterpret_cast<ScanStage*>(scan_smem);
     // block-shared scratch, double-buffered by iteration parity: with a single __syncthreads per tile a warp can
@@ -177,13 +215,16 @@ returns_scan_kernel(const float* __restrict__ rew, float* __restrict__ out, cons
                 const uint32_t tb = in ? (term[idx] != 0) : 1u;   // padding behaves like an episode end
                 tm[i >> 2] |= tb << (8 * (i & 3));
             }
+            // park the rewards in the thread's own stage slot like a full tile's (re-read in step 5)
+#pragma unroll
+            for (int q = 0; q < SCAN_ITEMS / 4; ++q)
+                *reinterpret_cast<float4*>(wx + sx_off(lane, q)) = make_float4(r[4 * q], r[4 * q + 1], r[4 * q + 2], r[4 * q + 3]);
         }
         // one bit per item (terminal bytes are 0/1: the append path normalises them)
         const uint32_t tbits = ((tm[0] * 0x01020408u) >> 24 & 0xfu) | (((tm[1] * 0x01020408u) >> 24 & 0xfu) << 4) |
                                (((tm[2] * 0x01020408u) >> 24 & 0xfu) << 8) | (((tm[3] * 0x01020408u) >> 24 & 0xfu) << 12);
         auto is_term = [&](int i) -> bool { return (tbits >> i) & 1u; };
 
-        if (!(dbg & 16)) {
         // 0. look-ahead (warp 0): the 128 transitions right of the tile, composed into one map.  With episodic
         //    data an episode end almost always lies inside it (A == 0), so the tile's incoming carry is known
         //    without waiting for any other CTA; only tiles inside very long episodes use the look-back below.
@@ -285,11 +326,11 @@ returns_scan_kernel(const float* __restrict__ rew, float* __restrict__ out, cons
         //    end, every thread reads the carry from shared memory and no second barrier is needed; thread 0
         //    publishes the tile's inclusive value off the critical path.  Otherwise (CTA-uniform branch) thread 0
         //    runs the decoupled look-back and the CTA waits for it.
-        const bool look_hit = (s_lookA == 0.0) && !(dbg & 8);
-        if (tid == 0) {
-            const Map tile = compose(Map{sA[0], sB[0]}, warp_excl);
+        const bool look_hit = (s_lookA == 0.0);
+        if (warp == 0) {
+            const Map tile = compose(Map{sA[0], sB[0]}, warp_excl);      // the same value in every lane of warp 0
             double carry = 0.0;
-            if (tile.A == 0.0) {       // an episode ends inside the tile: its inclusive value needs no carry
+            if (lane == 0 && tile.A == 0.0) {       // an episode ends inside the tile: its inclusive value needs no carry
                 sc.incl[t] = tile.B;
                 st_release_i32(sc.flags + t, 2);
             }
@@ -297,27 +338,20 @@ returns_scan_kernel(const float* __restrict__ rew, float* __restrict__ out, cons
                 carry = s_lookB;       // the value of the recurrence at the first transition right of the tile
             } else if (t > 0) {
                 // decoupled look-back over the tiles to the right: lower tile ids, i.e. earlier iterations of
-                // co-resident CTAs (or lower block ids in the same iteration), which never wait on this one
-                if (tile.A != 0.0) {
+                // co-resident CTAs (or lower block ids in the same iteration), which never wait on this one.  Inside a
+                // very long episode every tile waits for its predecessors; the chain of inclusive values advances 32
+                // tiles per memory round trip (warp-wide look-back) instead of one.
+                if (lane == 0 && tile.A != 0.0) {
                     sc.aggA[t] = tile.A; sc.aggB[t] = tile.B;
                     st_release_i32(sc.flags + t, 1);
                 }
-                Map cur{1.0, 0.0};
-                int j = t - 1;
-                while (!(dbg & 1)) {
-                    int f;
-                    while ((f = ld_acquire_i32(sc.flags + j)) == 0) { __nanosleep(20); }
-                    if (f == 2) { carry = __dadd_rn(cur.B, __dmul_rn(cur.A, __ldcg(sc.incl + j))); break; }
-                    cur = compose(cur, Map{__ldcg(sc.aggA + j), __ldcg(sc.aggB + j)});
-                    if (cur.A == 0.0) { carry = cur.B; break; }
-                    --j;   // j >= 0 always holds: tile 0 publishes an inclusive value
-                }
+                carry = warp_lookback(sc, t, lane);
             }
-            if (tile.A != 0.0) {
+            if (lane == 0 && tile.A != 0.0) {
                 sc.incl[t] = __dadd_rn(tile.B, __dmul_rn(tile.A, carry));
                 st_release_i32(sc.flags + t, 2);
             }
-            if (!look_hit) s_carry = carry;
+            if (!look_hit && lane == 0) s_carry = carry;
         }
         if (!look_hit) __syncthreads();
 
@@ -327,6 +361,15 @@ returns_scan_kernel(const float* __restrict__ rew, float* __restrict__ out, cons
         c = __dadd_rn(lane_excl.B, __dmul_rn(lane_excl.A, c));
         // the left half starts from the value at item 8 = right-half map applied to the carry
         const double c_lo = __dadd_rn(Bh, __dmul_rn(Ah, c));
+        // the rewards are re-read from the stage (the thread's own slot) instead of being held in 16 registers across
+        // the barrier and the look-back: the kernel runs at 64 registers per thread (4 CTAs per SM)
+#pragma unroll
+        for (int q = 0; q < SCAN_ITEMS / 4; ++q) {
+            float4 v;
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                         : "r"((uint32_t)__cvta_generic_to_shared(wx + sx_off(lane, q))));
+            r[4 * q + 0] = v.x; r[4 * q + 1] = v.y; r[4 * q + 2] = v.z; r[4 * q + 3] = v.w;
+        }
         if (F32CARRY) {
             const float gf = (float)g;
             float vh = (float)c, vl = (float)c_lo;
@@ -351,7 +394,6 @@ returns_scan_kernel(const float* __restrict__ rew, float* __restrict__ out, cons
                 r[i] = (float)vl;
             }
         }
-        }   // dbg & 16
         float lsum = 0.0f, lsq = 0.0f;
         if (full_tile) {
             // back through the (now free) stage for coalesced 128-bit stores
@@ -375,7 +417,7 @@ returns_scan_kernel(const float* __restrict__ rew, float* __restrict__ out, cons
 
         // 6. K2 statistics of the returns: one {sum, sumsq} pair per warp (fp32 partials over the warp's 512 values,
         //    Float64 from there on, folded in a fixed order by norm_finalize_kernel => deterministic)
-        if (tile_stats != nullptr && !(dbg & 4)) {
+        if (tile_stats != nullptr) {
 #pragma unroll
             for (int d = 16; d > 0; d >>= 1) {
                 lsum += __shfl_down_sync(0xffffffffu, lsum, d);
@@ -440,7 +482,6 @@ size_t scan_scratch_bytes(int64_t n) {
     return 16 + (size_t)round_up(tiles * 4, 16) + (size_t)tiles * 3 * sizeof(double);
 }
 
-int g_scan_dbg = 0;
 int launch_returns_scan(ppo_ctx* ctx, const float* reward_in, float* returns_out, const uint8_t* terminal, int64_t n,
                         double discount, int discount_is_f32, double* tile_stats, void* scratch) {
     PPO_REQUIRE(reward_in != returns_out, "returns scan runs out of place (the look-ahead reads its right neighbours' rewards)");
@@ -462,7 +503,7 @@ int launch_returns_scan(ppo_ctx* ctx, const float* reward_in, float* returns_out
         PPO_REQUIRE(occ >= 1, "returns scan: kernel does not fit on an SM");
         const int64_t grid = std::min<int64_t>(tiles, (int64_t)ctx->num_sms * occ);
         kern<<<(unsigned)grid, SCAN_THREADS, smem, ctx->stream>>>(reward_in, returns_out, terminal, n, g, g8, (int)tiles, sc,
-                                                                  tile_stats, g_scan_dbg);
+                                                                  tile_stats);
         return PPO_OK;
     };
     if (discount_is_f32) PPO_TRY(g1 ? launch(returns_scan_kernel<true, true>) : launch(returns_scan_kernel<true, false>));

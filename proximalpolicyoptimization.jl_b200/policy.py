@@ -29,7 +29,7 @@ def _pp(arrays):
 
 class Policy:
     def __init__(self, in_channels, hidden_channels, num_hidden_layers, num_output, ctx: Context | None = None,
-                 rng=None, weights=None, biases=None, leaky_slope=LEAKY_SLOPE):
+                 rng=None, weights=None, biases=None, leaky_slope=LEAKY_SLOPE, gemm_mode=None):
         self.ctx = ctx or default_context()
         self.hidden_channels, self.num_hidden_layers = hidden_channels, num_hidden_layers
         self.dims = [int(in_channels)] + [int(hidden_channels)] * int(num_hidden_layers) + [int(num_output)]
@@ -54,6 +54,9 @@ class Policy:
         self._h = h
         self._optimisers = weakref.WeakSet()
         self.ctx.adopt(self)
+        # the library's default engine is GEMM_AUTO (fastest fp32-parity engine whose shape contract the policy meets)
+        if gemm_mode is not None:
+            self.set_gemm_mode(gemm_mode)
 
     @property
     def handle(self):
@@ -82,6 +85,13 @@ class Policy:
         meets (fp16-split tcgen05, else 3xTF32 tcgen05, else fp32 FFMA); returns the engine in use."""
         _lib.check(_lib.load().ppo_policy_set_gemm_mode(self.handle, int(mode)))
         return self.gemm_mode
+
+    def read_gates(self, layer: int, rows: int):
+        """leakyrelu' branches (1 = positive) the last backward pass applied to hidden activation ``layer``
+        (1..L-1): uint8 [rows, dims[layer]] (parity instrumentation, see include/ppo_b200.h)."""
+        out = np.empty((int(rows), self.dims[layer]), np.uint8)
+        _lib.check(_lib.load().ppo_policy_read_gates(self.handle, int(layer), int(rows), _lib.ptr(out, C.c_uint8)))
+        return out
 
     def p2p_export(self) -> bytes:
         buf = C.create_string_buffer(64)

@@ -63,6 +63,9 @@ CONFIGS = {
     # tiny shapes for tests
     "t0": Config("t0-tiny", 90, 257, 8, 3, 4, 16, 2, 50),
     "t1": Config("t1-small", 91, 1000, 12, 16, 4, 32, 3, 128),
+    # small shape INSIDE the fp16-split tensor-core engine's contract (in % 8, hidden % 32): what PPO_GEMM_AUTO runs
+    # the benchmark configs on, at test size
+    "t2": Config("t2-f16", 93, 1024, 16, 8, 4, 64, 2, 256),
 }
 
 

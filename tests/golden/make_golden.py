@@ -70,3 +70,4 @@ if __name__ == "__main__":
     oracle_case("oracle_t0_g1", "t0", 1.0)
     oracle_case("oracle_t0_g099", "t0", 0.99)
     oracle_case("oracle_t1_g1", "t1", 1.0)
+    oracle_case("oracle_t2_g1", "t2", 1.0)

@@ -10,9 +10,12 @@ import pytest
 
 pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+# the fp32 FFMA engine on t1; the fp16-split tensor-core engine (what bench.py / SCALE time, with its per-layer overlapped
+# NCCL all-reduce or the peer-memory exchange, under CUDA-graph replay) on t2, a shape inside its contract
+_CFG = {"ffma": "t1", "f16x3": "t2"}
 
 
-def _worker(rank, world, port, q, p2p=False):
+def _worker(rank, world, port, q, p2p=False, engine="ffma"):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     sys.path.insert(0, ROOT)
     import torch
@@ -24,7 +27,7 @@ def _worker(rank, world, port, q, p2p=False):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     ctx = P.Context(rank)
     D.init_comm(ctx)
-    cfg = S.CONFIGS["t1"]
+    cfg = S.CONFIGS[_CFG[engine]]
     data = S.make_buffer(cfg)
     W, b = S.make_weights(cfg)
     old = S.rng_for(cfg, 7).uniform(0.05, 1.0, cfg.N).astype(np.float32)
@@ -37,7 +40,9 @@ def _worker(rank, world, port, q, p2p=False):
     ret = P.compute_returns(data["reward"][full], data["terminal"][full], 1.0, ctx)[:n_use]
     buf = P.DeviceRollouts(cfg.nf, cfg.nhe, cfg.apa, n_use, ctx)
     buf.append(data["feat"][sl], data["mask"][sl], old[sl], data["action"][sl], ret, data["terminal"][sl])
-    pol = P.Policy(cfg.nf, cfg.H, cfg.L, cfg.apa, ctx, weights=W, biases=b)
+    mode = {"ffma": P.GEMM_FP32_SIMT, "f16x3": P.GEMM_F16X3_TC}[engine]
+    pol = P.Policy(cfg.nf, cfg.H, cfg.L, cfg.apa, ctx, weights=W, biases=b, gemm_mode=mode)
+    assert pol.gemm_mode == mode
     if p2p:
         assert D.enable_p2p_gradients(pol)
     opt = P.Adam(1e-4)
@@ -50,9 +55,11 @@ def _worker(rank, world, port, q, p2p=False):
     dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("engine", ["ffma", "f16x3"])
 @pytest.mark.parametrize("p2p", [False, True], ids=["nccl", "peer-memory"])
-def test_two_rank_epoch_matches_sharded_oracle(p2p):
-    """p2p = True: the gradient exchange over CUDA-IPC peer memory fused into Adam (csrc/dp_p2p.cu) instead of NCCL"""
+def test_two_rank_epoch_matches_sharded_oracle(p2p, engine):
+    """p2p = True: the gradient exchange over CUDA-IPC peer memory fused into Adam (csrc/dp_p2p.cu) instead of NCCL
+    (fp16-split engine + NCCL = the per-layer all-reduce overlapped with the backward pass)"""
     import torch
     if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
@@ -64,8 +71,8 @@ def test_two_rank_epoch_matches_sharded_oracle(p2p):
     world = 2
     mctx = mp.get_context("spawn")
     q = mctx.Queue()
-    port = 29600 + (os.getpid() % 1000)
-    procs = [mctx.Process(target=_worker, args=(r, world, port + (7 if p2p else 0), q, p2p)) for r in range(world)]
+    port = 29600 + (os.getpid() % 1000) + (7 if p2p else 0) + (13 if engine == "f16x3" else 0)
+    procs = [mctx.Process(target=_worker, args=(r, world, port, q, p2p, engine)) for r in range(world)]
     [p.start() for p in procs]
     res = {}
     for _ in range(world):
@@ -74,7 +81,7 @@ def test_two_rank_epoch_matches_sharded_oracle(p2p):
     [p.join(60) for p in procs]
     assert all(p.exitcode == 0 for p in procs)
     # ---- CPU restatement of the sharded scheme ----
-    cfg = S.CONFIGS["t1"]
+    cfg = S.CONFIGS[_CFG[engine]]
     data = S.make_buffer(cfg)
     W, b = S.make_weights(cfg)
     old = S.rng_for(cfg, 7).uniform(0.05, 1.0, cfg.N).astype(np.float32)

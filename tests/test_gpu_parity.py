@@ -242,7 +242,13 @@ def _grad_tol(got, want, rel=1e-5):
     return np.max(np.abs(got - want)) <= rel * np.max(np.abs(want)) + 1e-7
 
 
-@pytest.mark.parametrize("name,key", [("oracle_t0_g1", "t0"), ("oracle_t0_g099", "t0"), ("oracle_t1_g1", "t1")])
+# engines PPO_GEMM_AUTO (the default of a new policy) resolves to: t0 is outside both tensor-core contracts, t1 inside
+# the tf32 engine's, t2 inside the fp16-split engine's (the one the benchmark configs run on)
+_AUTO_ENGINE = {"t0": P.GEMM_FP32_SIMT, "t1": P.GEMM_TF32X3_TC, "t2": P.GEMM_F16X3_TC}
+
+
+@pytest.mark.parametrize("name,key", [("oracle_t0_g1", "t0"), ("oracle_t0_g099", "t0"), ("oracle_t1_g1", "t1"),
+                                      ("oracle_t2_g1", "t2")])
 def test_golden_minibatch_and_epoch(ctx, name, key):
     z = np.load(os.path.join(G, name + ".npz"))
     cfg = S.CONFIGS[key]
@@ -259,6 +265,7 @@ def test_golden_minibatch_and_epoch(ctx, name, key):
         assert np.all(np.abs(got_ret - z["returns"]) <= 1e-6 + 1e-5 * np.abs(z["returns"]))
     assert np.array_equal(buf.generate_permutation(int(z["seed"]), want=True) - 1, z["perm0"])
     pol = P.Policy(cfg.nf, cfg.H, cfg.L, cfg.apa, ctx, weights=W, biases=b)
+    assert pol.gemm_mode == _AUTO_ENGINE[key]
     ds = P.construct_dataset(buf)
     # first minibatch through step_batch! on host arrays (gradient only)
     batch = gather_minibatch(ds, 0, cfg.B)

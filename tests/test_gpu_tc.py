@@ -1,6 +1,7 @@
 """tcgen05 engines (PPO_GEMM_TF32X3_TC: 3xTF32 split; PPO_GEMM_F16X3_TC: scaled fp16 hi/lo split): the
 error-compensated GEMMs against fp64 numpy and the whole update against the oracle, at the stated fp32
-tolerance (1e-5 of the tensor's max-abs)."""
+tolerance (1e-5 of the tensor's max-abs).  Whole-network gradients against the Float64 oracle (many seeds, the reference's
+leakyrelu slope, full C3 minibatch): tests/test_gpu_engine_parity.py."""
 import ctypes as C
 import os
 
@@ -72,78 +73,26 @@ def test_dense_ops_vs_fp64(ctx, mode, M, K, N):
             assert np.max(np.abs(got2[:K] - cs)) <= 1e-5 * np.max(np.abs(cs)) + 1e-6
 
 
+@pytest.mark.parametrize("M,K,N", [(4096, 512, 512), (2048, 1024, 256)])
+def test_f16_engine_all_positive_operands(ctx, M, K, N):
+    """Operands of one sign are the worst case for the tensor core's round-toward-zero accumulation (every add of a chain
+    loses in the same direction: up to ~n/2 * 2^-24 of the sum over an n-MMA chain).  The compensated fold
+    (KK16Params::rz_comp) is a statistical correction calibrated on mixed-sign data; the 1e-5 bound must hold with a wide
+    margin here too, so the constant is a refinement, not what parity rests on."""
+    rng = np.random.default_rng(M + K)
+    X = np.abs(rng.normal(size=(M, K))).astype(np.float32)
+    W = np.abs(rng.normal(size=(K, N)) / np.sqrt(K)).astype(np.float32)
+    b = np.abs(rng.normal(size=N)).astype(np.float32)
+    dY = np.abs(rng.normal(size=(M, N))).astype(np.float32)
+    for op in (0, 1, 2):
+        got, _ = dense(ctx, F16, op, X, W, b, dY)
+        want = truth(op, X, W, b, dY)
+        err = np.max(np.abs(got - want)) / np.max(np.abs(want))
+        assert err <= 3e-6, (op, err)
+
+
 def _flat(W, b):
     return np.concatenate([np.concatenate([w.ravel(), x.ravel()]) for w, x in zip(W, b)])
-
-
-def _c3_case(nb, seed):
-    cfg = S.CONFIGS["c3"]
-    rng = np.random.default_rng(seed)
-    feat = rng.integers(-3, 9, (nb, cfg.nhe, cfg.nf)).astype(np.float32)
-    mask = S.make_masks(rng, nb, cfg.nhe, cfg.apa)
-    act = S.make_actions(rng, mask)
-    W, b = S.make_weights(cfg)
-    b = [x + rng.normal(0, 0.05, x.shape).astype(np.float32) for x in b]
-    adv = rng.integers(-4, 5, nb).astype(np.float32)
-    return cfg, rng, feat, mask, act, W, b, adv
-
-
-def _tensor_errors(cfg, got, want):
-    """max-abs error of every parameter tensor relative to that tensor's max-abs."""
-    out, off = [], 0
-    d = cfg.dims
-    for i, o in zip(d[:-1], d[1:]):
-        for size in (i * o, o):
-            w = want[off:off + size]
-            out.append(np.max(np.abs(got[off:off + size] - w)) / (np.max(np.abs(w)) + 1e-30))
-            off += size
-    return out
-
-
-@pytest.mark.parametrize("slope", [1.0, 0.01])
-def test_policy_gradient_c3_widths(ctx, slope):
-    """MLP 3x512 on 64 features x 16 tokens (config C3 shapes), 512 samples.
-
-    slope = 1.0: leakyrelu is the identity, the loss is smooth in the weights, and ALL engines must match
-    the fp64 oracle to 1e-5 of every parameter tensor's max-abs.
-    slope = 0.01 (the reference's): leakyrelu' is discontinuous at 0, so two evaluations that round differently
-    (fp64 oracle, fp32 FFMA, either tensor-core engine) can take different branches for a pre-activation within
-    rounding of zero; ONE such flip on a token with a large advantage/old-probability ratio is a rank-1 change of
-    every gradient tensor below it (scripts/f16_diag2.py: about half of all seeds show one, for either engine, at
-    the same rate).  The fp64 oracle is therefore matched at 1e-5 for the LOSS, and the tensor-core engines are held
-    to the fp32 FFMA engine at 1e-5 of every tensor's max-abs on a seed where no influential pre-activation sits
-    within rounding of zero (73; deterministic kernels make this stable).
-    """
-    cfg, rng, feat, mask, act, W, b, adv = _c3_case(512, 73)
-    nb = feat.shape[0]
-    o64 = O.Policy(cfg.nf, cfg.H, cfg.L, cfg.apa)
-    o64.slope = slope
-    o64.W, o64.b = [w.astype(np.float64) for w in W], [x.astype(np.float64) for x in b]
-    probs = O.batch_action_probabilities(o64, feat.astype(np.float64), mask.astype(np.float64))
-    old = (probs[np.arange(nb), act - 1] * np.exp(rng.normal(0, 0.1, nb))).clip(1e-6, 1).astype(np.float32)
-    pl, ew, dW, db = O.policy_gradient(o64, feat.astype(np.float64), mask.astype(np.float64), act,
-                                       old.astype(np.float64), adv.astype(np.float64), 0.05, 0.01)
-    want = _flat(dW, db)
-    lin = P.get_linear_action_index(act, cfg.A)
-    res = {}
-    for mode in (SIMT, TC, F16):
-        pol = P.Policy(cfg.nf, cfg.H, cfg.L, cfg.apa, ctx, weights=W, biases=b, leaky_slope=slope)
-        pol.set_gemm_mode(mode)
-        gp, ge, grads = P.step_batch_(pol, None, P.StateData(feat, mask), lin, old, adv, 0.05, 0.01, return_grads=True)
-        # ppoloss = -mean(min(gain, clip)) is a mean of +-|adv|-sized terms that nearly cancels (|loss| ~ 1e-2 of the
-        # term size): the fp32 bound is 1e-5 of the loss plus 1e-6 of the mean term magnitude
-        assert abs(gp - pl) <= 1e-5 * abs(pl) + 1e-6 * float(np.mean(np.abs(adv))), (mode, gp, pl)
-        assert abs(ge - ew) <= 1e-5 * abs(ew) + 1e-8
-        res[mode] = grads
-        pol.close()
-    if slope == 1.0:
-        for mode in (SIMT, TC, F16):
-            errs = _tensor_errors(cfg, res[mode], want)
-            assert max(errs) <= 1e-5, (mode, errs)
-    else:
-        for mode in (TC, F16):
-            errs = _tensor_errors(cfg, res[mode], res[SIMT].astype(np.float64))
-            assert max(errs) <= 1e-5, (mode, errs)
 
 
 def test_tc_mode_refuses_unsupported_shapes_loudly(ctx):
@@ -230,10 +179,11 @@ def test_golden_epoch_tc_mode(ctx, name, key):
 
 
 def test_gemm_auto_picks_the_fastest_engine_inside_its_contract(ctx):
-    for key, want in (("t0", SIMT), ("t1", TC), ("c3", F16), ("c2", F16)):
+    for key, want in (("t0", SIMT), ("t1", TC), ("t2", F16), ("c3", F16), ("c2", F16)):
         cfg = S.CONFIGS[key]
         W, b = S.make_weights(cfg)
         pol = P.Policy(cfg.nf, cfg.H, cfg.L, cfg.apa, ctx, weights=W, biases=b)
-        assert pol.gemm_mode == SIMT
+        assert pol.gemm_mode == want, key          # PPO_GEMM_AUTO is the default of a new policy
+        assert pol.set_gemm_mode(SIMT) == SIMT
         assert pol.set_gemm_mode(P.GEMM_AUTO) == want, key
         pol.close()
