@@ -2,29 +2,43 @@
 """bench.py — PPO-update samples/s on B200 (metric of BASELINE.json), one JSON line on stdout.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--gemm fp32|tf32x3|f16x3]
+                    [--config c3] [--batch B] [--scaling weak|strong] [--e2e-feat i8|f32] [--profile] [--no-extras]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-A "step" is one pass of the hot path over one filled rollout buffer: returns scan over the whole
-buffer (K1) + device permutation (K3) + ONE PPO epoch = ceil(N/B) minibatches of gather (K4) ->
-MLP forward (K5) -> fused loss (K6) -> MLP backward (K7) -> [NCCL grad all-reduce] -> Adam (K8).
-`value` = transitions processed by all ranks / device time (CUDA events on the library's stream,
-max over ranks) with the buffer resident in HBM; `e2e` = the same through the public API with HOST
-(pinned) buffers: the H2D append of the whole buffer and the D2H read of the losses are inside the
-timed region.  N=1 workload: config C3 (1M transitions, MLP 3x512, B=65536).  N>1: every rank holds
-a C3-sized shard (weak scaling; at N=8 this is C4: 8M transitions, global B=65536, B/N rows per
-rank) and the minibatch gradients are summed over the ranks inside the Adam kernel through NVLink
-peer memory (CUDA IPC; PPO_B200_NO_P2P=1 selects the NCCL all-reduce instead).
+A "step" is one pass of the hot path over one filled rollout buffer: returns scan over the whole buffer (K1) + device
+permutation (K3) + ONE PPO epoch = ceil(N/B) minibatches of gather (K4) -> MLP forward (K5) -> fused loss (K6) -> MLP
+backward (K7) -> [gradient exchange] -> Adam (K8).
+`value` = transitions processed by all ranks / device time (CUDA events on the library's stream, max over ranks) with the
+buffer resident in HBM; `e2e` = the same through the public API with HOST (pinned) buffers, timed over the same number
+of steps: the H2D append of the whole buffer and the D2H read of the losses are inside the timed region.  The host
+features are the small integers a quad-game state holds (Matrix{Int64} in the reference), handed over as Int8 through
+ppo_buffer_append_i8 (--e2e-feat f32: as Float32, 4x the bytes).
+N=1 workload: config C3 (1M transitions, MLP 3x512, B=65536).  N>1: every rank holds a C3-sized shard (weak scaling; at
+N=8 this IS config C4: 8M transitions in total, global B=65536, B/N rows per rank); --scaling strong runs C4 as written
+at any N (8 388 608 transitions in total, N/G per rank).  The minibatch gradients are summed over the ranks inside the Adam
+kernel through NVLink peer memory (CUDA IPC; PPO_B200_NO_P2P=1 selects the NCCL all-reduce instead).
 
---impl reference times the CPU restatement of the reference (oracle/: Julia is not installable in
-this image) on a bounded sample of the same workload with all host threads.
+Besides the headline the line carries (each measured live in this run):
+  roofline      dominant kernel (hidden Dense forward GEMM) + roofline.hbm (scan / gather / loss fractions of the HBM peak)
+                + roofline.traffic from an ncu replay of that kernel launched by this script (null when ncu is unusable)
+  cpu_baseline  the restated CPU path (oracle port) on a bounded sample, rank 0 at N=1
+  configs       the other named configs: C2 (65k transitions, Policy(72,128,2,4)) at B=32 and B=4096, C5 (disk replay)
+  dp_parity     N>1: a short sharded epoch after the timed region — replicas bit-identical, losses / weights vs the
+                CPU restatement of the sharded scheme on rank 0
+
+--impl reference times the CPU restatement of the reference (oracle/: Julia is not installable in this image) on a
+bounded sample of the same workload with all host threads.
 """
 from __future__ import annotations
 
 import argparse
+import dataclasses
 import json
 import os
+import shutil
 import subprocess
 import sys
+import tempfile
 import threading
 import time
 
@@ -36,6 +50,7 @@ sys.path.insert(0, ROOT)
 METRIC = "ppo_update_samples_per_s"
 UNIT = "samples/s"
 EPS, W_ENT, ETA, GAMMA = 0.05, 0.01, 1e-4, 1.0
+C4_TOTAL = 8388608
 
 
 def log(*a):
@@ -95,10 +110,39 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def workload(args):
+    """(cfg of one rank's shard, local minibatch rows, static `config` object) — shared by both arms so that the
+    reference arm's line describes exactly the same workload."""
+    from ppo_b200 import synthetic as S
+    world = max(1, args.gpus)
+    cfg = S.CONFIGS[args.config]
+    name = cfg.name
+    if args.scaling == "strong":
+        assert C4_TOTAL % world == 0
+        cfg = dataclasses.replace(S.CONFIGS["c4"], N=C4_TOTAL // world)
+        name = f"{S.CONFIGS['c4'].name} ({C4_TOTAL} transitions in total, {cfg.N} per GPU)"
+    elif world > 1:
+        name = f"{cfg.name} x{world} shards" + (" (= config C4: 8M transitions in total)" if world == 8 and args.config == "c3" else "")
+    B_local = max(1, (args.batch or cfg.B) // world)
+    config = {
+        "workload": name, "transitions_per_gpu": cfg.N, "minibatch_rows_per_gpu": B_local,
+        "global_minibatch": B_local * world, "mlp": f"{cfg.L}x{cfg.H}", "nf": cfg.nf, "nhe": cfg.nhe,
+        "actions_per_state": cfg.A, "epochs_per_step": 1, "gemm_engine": args.gemm,
+        "parallelism": f"dp{world}" if world > 1 else "single",
+        "grad_exchange": (("nccl all-reduce" if os.environ.get("PPO_B200_NO_P2P", "0") == "1" else
+                           "nvlink peer memory, fused into the Adam kernel") if world > 1 else None),
+        "host_features": {"i8": "int8 (ppo_buffer_append_i8)", "f32": "float32 (ppo_buffer_append)"}[args.e2e_feat],
+        "l2": "step inputs exceed L2; per-kernel timings flush L2 between launches (write 256 MB, then read 256 MB)",
+    }
+    return cfg, B_local, config
+
+
 # ----------------------------------------------------------------------------------------------
-def cpu_reference_step(cfg, data, W, b, rows, threads):
-    """The restated CPU path (oracle port) on `rows` transitions of the workload: serial returns scan
-    (C), record-copy gather (C), fp32 MLP through the host BLAS, unfused loss, Adam.  Returns seconds."""
+# CPU arm (oracle port)
+# ----------------------------------------------------------------------------------------------
+def cpu_reference_step(cfg, data, W, b, rows):
+    """The restated CPU path (oracle port) on `rows` transitions of the workload: serial returns scan (C), record-copy
+    gather (C), fp32 MLP through the host BLAS, unfused loss, Adam.  Returns seconds."""
     from oracle import c_oracle as CO
     from oracle import ppo_oracle as O
     t0 = time.perf_counter()
@@ -132,27 +176,50 @@ def host_blas_threads(want_all=False):
     return None, (max(info) if info else 1)
 
 
-def cpu_baseline(cfg, data, W, b, target_s=12.0):
+def cpu_sample_data(cfg, n_sub):
+    """First n_sub transitions of the workload as the oracle's (Float32) arrays, old probabilities drawn by the same
+    generator as the GPU arm from the CPU restatement's own forward pass at the initial weights."""
+    from ppo_b200 import synthetic as S
+    from oracle import ppo_oracle as O
+    small = dataclasses.replace(cfg, N=n_sub)
+    data = S.make_buffer(small)
+    W, b = S.make_weights(cfg)
+    pol = O.Policy(cfg.nf, cfg.H, cfg.L, cfg.apa)
+    pol.W, pol.b = [w.copy() for w in W], [x.copy() for x in b]
+    sel = np.empty(n_sub, np.float32)
+    for s in range(0, n_sub, 4096):
+        e = min(n_sub, s + 4096)
+        pr = O.batch_action_probabilities(pol, data["feat"][s:e], data["mask"][s:e])
+        sel[s:e] = pr[np.arange(e - s), data["action"][s:e] - 1]
+    data["old"] = S.make_old_probs(small, sel)
+    return data, W, b
+
+
+def cpu_baseline(cfg, target_s=12.0):
     _, threads = host_blas_threads()
-    rows = min(2048, cfg.B)
-    t = cpu_reference_step(cfg, data, W, b, rows, threads)
+    n_sub = min(cfg.N, 65536)
+    data, W, b = cpu_sample_data(cfg, n_sub)
+    rows = min(2048, cfg.B, n_sub)
+    t = cpu_reference_step(cfg, data, W, b, rows)
     rate = rows / t
-    rows2 = int(min(cfg.B, max(rows, rate * target_s)))
+    rows2 = int(min(cfg.B, n_sub, max(rows, rate * target_s)))
     if rows2 > rows * 2:
-        t = cpu_reference_step(cfg, data, W, b, rows2, threads)
+        t = cpu_reference_step(cfg, data, W, b, rows2)
         rows = rows2
     return {"value": rows / t, "unit": UNIT, "cores": threads, "kind": "port",
-            "sample": f"{rows} of {cfg.N} transitions: C scan share + C gather + numpy/BLAS fp32 MLP fwd/bwd + "
-                      f"unfused loss + Adam (oracle port; Julia not installable here), {t:.2f} s"}
+            "sample": f"one minibatch of {rows} transitions out of the first {n_sub} of config {cfg.name}: C scan share + C "
+                      f"gather + numpy/BLAS fp32 MLP fwd/bwd + unfused loss + Adam (oracle port; Julia not installable "
+                      f"here), {t:.2f} s"}
 
 
 # ----------------------------------------------------------------------------------------------
-def make_data(cfg, P, S, ctx, W, b, rank, cheap_old=False):
-    """Synthetic buffer (host, pinned) + old probabilities from the policy's own forward at the
-    initial weights, computed by the device path in chunks (outside every timed region)."""
+# synthetic data in pinned host memory
+# ----------------------------------------------------------------------------------------------
+def make_data(cfg, P, S, ctx, W, b, rank, feat_dtype=np.int8, cheap_old=False):
+    """Synthetic buffer (host, pinned; features as small integers of `feat_dtype`) + old probabilities from the policy's
+    own forward at the initial weights, computed by the device path in chunks (outside every timed region)."""
     import torch
     t0 = time.perf_counter()
-    import dataclasses
     cfg_r = dataclasses.replace(cfg, cid=cfg.cid + 100 * rank)     # a different shard per rank
     pinned = {}
 
@@ -161,7 +228,7 @@ def make_data(cfg, P, S, ctx, W, b, rank, cheap_old=False):
         pinned[len(pinned)] = tt          # keep the pinned storage alive
         return tt.numpy()
 
-    data = S.make_buffer(cfg_r, alloc=alloc)      # generated in place in pinned host memory (no second copy)
+    data = S.make_buffer(cfg_r, alloc=alloc, feat_dtype=feat_dtype)   # generated in place in pinned host memory
     term = alloc(data["terminal"].shape, np.uint8)
     term[:] = data["terminal"]
     data["terminal"] = term
@@ -174,17 +241,18 @@ def make_data(cfg, P, S, ctx, W, b, rank, cheap_old=False):
         chunk = 32768
         for s in range(0, cfg.N, chunk):
             e = min(cfg.N, s + chunk)
-            pr = P.batch_action_probabilities(pol, P.StateData(data["feat"][s:e], data["mask"][s:e]))
+            pr = P.batch_action_probabilities(pol, P.StateData(data["feat"][s:e].astype(np.float32), data["mask"][s:e]))
             sel[s:e] = pr[np.arange(e - s), data["action"][s:e] - 1]
         pol.close()
-    old = S.make_old_probs(cfg_r, sel)
-    po = torch.empty(cfg.N, dtype=torch.float32, pin_memory=True)
-    po.numpy()[...] = old
-    data["old"] = po.numpy()
-    data["_pins"]["old"] = po
-    data["_keep"] = None
-    log(f"[rank {rank}] synthetic data ready in {time.perf_counter() - t0:.1f} s")
+    old = alloc((cfg.N,), np.float32)
+    old[...] = S.make_old_probs(cfg_r, sel)
+    data["old"] = old
+    log(f"[rank {rank}] synthetic data for {cfg.name} ready in {time.perf_counter() - t0:.1f} s")
     return data
+
+
+def host_bytes_per_transition(cfg, feat_dtype):
+    return np.dtype(feat_dtype).itemsize * cfg.nf * cfg.nhe + 4 * cfg.A + 8 + 4 + 4 + 1
 
 
 class _StdoutToStderr:
@@ -203,6 +271,356 @@ class _StdoutToStderr:
         os.close(self.saved)
 
 
+class Harness:
+    """process-wide handles + the timing loop (barrier + synchronize on both sides, CUDA events on the library's stream,
+    max over ranks)"""
+
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+        import ppo_b200 as P
+        from ppo_b200 import distributed as D
+        from ppo_b200 import synthetic as S
+        self.torch, self.dist, self.P, self.D, self.S = torch, dist, P, D, S
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        if self.world > 1:
+            dist.init_process_group("cpu:gloo,cuda:nccl", rank=self.rank, world_size=self.world)
+        torch.cuda.set_device(self.local_rank)
+        self.ctx = P.Context(self.local_rank)
+        if self.world > 1:
+            D.init_comm(self.ctx)
+        self.stream = torch.cuda.ExternalStream(self.ctx.stream())
+        self.use_p2p = self.world > 1 and os.environ.get("PPO_B200_NO_P2P", "0") != "1"
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def timed(self, fn, steps, warmup, tag, sample_clocks=False):
+        torch = self.torch
+        for i in range(warmup):
+            fn(i)
+        self.barrier()
+        sampler = ClockSampler(self.local_rank) if sample_clocks else None
+        if sampler:
+            sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = self.ctx.launch_count()
+        t0 = time.perf_counter()
+        e0.record(self.stream)
+        for i in range(steps):
+            fn(warmup + i)
+        e1.record(self.stream)
+        self.barrier()
+        wall = time.perf_counter() - t0
+        ms = e0.elapsed_time(e1)
+        clocks = sampler.stop() if sampler else None
+        launches = self.ctx.launch_count() - l0
+        if self.world > 1:
+            t = torch.tensor([ms], dtype=torch.float64)
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+            ms = float(t.item())
+        log(f"[rank {self.rank}] {tag}: {ms / steps:.3f} ms/step (events), wall {1e3 * wall / steps:.3f} ms/step")
+        return ms / steps, clocks, launches
+
+
+def run_update_legs(h, cfg, B_local, gemm_mode, data, W, b, steps, warmup, feat_key="feat", sample_clocks=True, e2e=True):
+    """resident + end-to-end legs of one workload; returns a dict of raw measurements"""
+    P = h.P
+    pol = P.Policy(cfg.nf, cfg.H, cfg.L, cfg.apa, h.ctx, weights=W, biases=b, gemm_mode=gemm_mode)
+    if h.use_p2p:
+        h.D.enable_p2p_gradients(pol)
+    opt = P.Optimiser(P.Adam(ETA))
+    buf = P.DeviceRollouts(cfg.nf, cfg.nhe, cfg.apa, cfg.N, h.ctx)
+    last = {}
+
+    def fill():
+        buf.clear()
+        buf.append(data[feat_key], data["mask"], data["old"], data["action"], data["reward"], data["terminal"])
+
+    def update(seed):
+        P.compute_state_value_(buf, GAMMA)
+        return P.ppo_train_(pol, opt, P.construct_dataset(buf), EPS, B_local, 1, W_ENT, seed=seed, out=None)
+
+    fill()
+    buf.save_rewards()
+
+    def resident_step(i):
+        buf.restore_rewards()
+        last["loss"] = update(1000 + i)
+
+    ms_step, clocks, launches = h.timed(resident_step, steps, warmup, f"{cfg.name} resident", sample_clocks)
+    out = {"ms_step": ms_step, "clocks": clocks, "launches": launches, "engine": pol.gemm_mode,
+           "nbatches": (cfg.N + B_local - 1) // B_local}
+    if e2e:
+        def e2e_step(i):
+            fill()
+            last["loss"] = update(2000 + i)
+
+        ms_e2e, _, _ = h.timed(e2e_step, steps, max(1, min(warmup, 2)), f"{cfg.name} e2e")
+        out["ms_e2e"] = ms_e2e
+    out["loss"] = [float(last["loss"][0][0]), float(last["loss"][1][0])]
+    pol.close(); buf.close()
+    return out
+
+
+# ----------------------------------------------------------------------------------------------
+# extra legs
+# ----------------------------------------------------------------------------------------------
+def kernel_rooflines(h, cfg, B_local, gemm):
+    """per-kernel rooflines, measured live with CUDA events on the library's stream (rank 0)"""
+    pk = peaks()
+    ctx = h.ctx
+    kernels = {}
+    M = B_local * cfg.nhe
+
+    def hbm(name, which, n, a=0, b_=0, c=0, iters=10):
+        ms, work = ctx.bench_kernel(which, n, a, b_, c, iters, True)
+        gbs = work / (ms * 1e-3) / 1e9
+        kernels[name] = {"bound": "hbm", "achieved": round(gbs, 1), "peak": pk["hbm"], "unit": "GB/s",
+                         "frac": round(gbs / pk["hbm"], 4), "ms": round(ms, 4), "bytes": work}
+        return kernels[name]
+
+    hbm("K1_scan_namedN", "scan", cfg.N, 15)
+    k1 = hbm("K1_scan_64M", "scan", 64 * 1024 * 1024, 15, iters=5)
+    k1g = hbm("K1_scan_64M_gamma0.99", "scan", 64 * 1024 * 1024, 15, 1, iters=5)
+    k2 = hbm("K1K2_scan_64M_with_norm_stats", "scan_norm", 64 * 1024 * 1024, 15, iters=5)
+    k1l = hbm("K1_scan_64M_longepisodes_gamma0.99", "scan", 64 * 1024 * 1024, 1 << 30, 1, iters=3)
+    hbm("K3_shuffle", "shuffle", cfg.N)
+    k4 = hbm("K4_gather_ldg", "gather0", cfg.N, cfg.nf * cfg.nhe, cfg.A, B_local)
+    hbm("K4_gather_bulk", "gather1", cfg.N, cfg.nf * cfg.nhe, cfg.A, B_local)
+    hbm("K6_loss_namedB", "loss", B_local, cfg.A)
+    k6 = hbm("K6_loss_1M", "loss", 1 << 20, cfg.A, iters=5)
+    hp = "head16" if gemm == "f16x3" else "head"     # the fp16-split engine has its own head kernels
+    hbm("K5_head_fwd", hp + "_fwd", M, cfg.H, cfg.apa, iters=5)
+    hbm("K7_head_bwd", hp + "_bwd", M, cfg.H, cfg.apa, iters=5)
+    hbm("K8_adam", "adam", cfg.num_params)
+    gname = {"fp32": "gemm", "tf32x3": "tc1", "f16x3": "tc3"}[gemm]
+    dom = {}
+    for kind in ("fwd", "dgrad", "wgrad"):
+        ms, flops = ctx.bench_kernel(f"{gname}_{kind}", M, cfg.H, cfg.H, 0, 3, True)
+        tf = flops / (ms * 1e-3) / 1e12
+        dom[kind] = {"ms": round(ms, 4), "tflops_fp32_equiv": round(tf, 2)}
+        kernels[f"K5K7_gemm_{kind}_{cfg.H}x{cfg.H}"] = {
+            "bound": "tensor", "achieved": round(tf, 2), "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
+            "frac": round(tf / pk["bf16_sustained"], 4), "ms": round(ms, 4), "flops": flops}
+    # The dominant kernel of the step: the hidden-layer forward/dgrad GEMM kernel (about half of the step in the ncu
+    # launch list).  `achieved` counts ALGORITHMIC flops (2 M K N of the fp32 GEMM it replaces); the error-compensated
+    # split issues 3x as many tensor flops (fp16 at the full bf16 rate, tf32 at half of it), so the scheme's own ceiling is
+    # peak / 3 (fp16) or peak / 6 (tf32).
+    fwd = dom["fwd"]
+    ach = fwd["tflops_fp32_equiv"]
+    passes = 3 if gemm in ("tf32x3", "f16x3") else 1
+    ceiling = pk["bf16_sustained"] / (6.0 if gemm == "tf32x3" else 3.0)
+    kname = {"tf32x3": "tc_gemm_kk_kernel<256>", "f16x3": "f16_gemm_kk_kernel<256, CTA pair>", "fp32": "sgemm_kernel"}[gemm]
+    roofline = {"bound": "tensor", "achieved": ach, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
+                "frac": round(ach / pk["bf16_sustained"], 4), "traffic": None,
+                "kernel": kname + f" (hidden Dense forward, M={M}, K=N={cfg.H})", "ms_per_launch": fwd["ms"],
+                "peak_source": pk["src"] + " bf16 sustained (MEASURED_PEAKS.json; kernel timed inside a long step)",
+                "tensor_flops_issued_tflops": round(ach * passes, 2),
+                "frac_of_3pass_ceiling": round(ach / ceiling, 4) if passes == 3 else None,
+                # the HBM-bound kernels of the path against the measured copy peak (>> L2 sizes; named sizes in `kernels`)
+                "hbm": {"peak_gbs": pk["hbm"], "K1_scan_64M": k1["frac"], "K1_scan_64M_gamma0.99": k1g["frac"],
+                        "K1K2_scan_with_norm_stats": k2["frac"], "K1_scan_64M_one_episode": k1l["frac"],
+                        "K4_gather": k4["frac"], "K6_loss_1M": k6["frac"]},
+                "detail": dom}
+    return roofline, kernels
+
+
+def ncu_traffic_probe(M, H, which="tc3_fwd"):
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel at the benchmark's shape, from an
+    ncu replay launched here (a separate tiny process: the timed numbers of this run are never taken under a profiler)"""
+    ncu = shutil.which("ncu") or "/usr/local/cuda/bin/ncu"
+    if not os.path.exists(ncu):
+        return None, "ncu not found"
+    code = (f"import sys; sys.path.insert(0, {ROOT!r}); import ppo_b200 as P; c = P.Context(0); "
+            f"c.bench_kernel({which!r}, {M}, {H}, {H}, 0, 1, False); c.close()")
+    cmd = [ncu, "--metrics", "dram__bytes_read.sum,dram__bytes_write.sum", "--clock-control", "none", "-k",
+           "regex:f16_gemm_kk|tc_gemm_kk|sgemm", "-c", "1", "--csv", sys.executable, "-c", code]
+    try:
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=240)
+    except Exception as e:   # noqa: BLE001
+        return None, f"ncu failed: {e}"
+    total, unit_scale = 0.0, {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    found = 0
+    for ln in r.stdout.splitlines():
+        if "dram__bytes_" not in ln:
+            continue
+        f = [x.strip('"') for x in ln.strip().split('","')]
+        try:
+            total += float(f[-1].replace(",", "")) * unit_scale.get(f[-2], 1.0)
+            found += 1
+        except (ValueError, IndexError):
+            continue
+    if found < 2:
+        return None, "ncu produced no dram__bytes rows: " + (r.stderr.strip().splitlines()[-1] if r.stderr.strip() else "empty output")
+    return total, "ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum replay of one launch, run by bench.py"
+
+
+def run_c2(h, args, gemm_mode):
+    """config C2: 65 536 transitions, Policy(72,128,2,4) on 64 half-edges (test/test_square_mesh.jl:29), at the
+    reference-like tiny minibatch and at B = 4096; one GPU"""
+    P, S = h.P, h.S
+    cfg = S.CONFIGS["c2"]
+    W, b = S.make_weights(cfg)
+    data = make_data(cfg, P, S, h.ctx, W, b, 0, np.int8)
+    out = {}
+    steps = max(1, min(args.steps, 5))
+    for B in (32, 4096):
+        r = run_update_legs(h, cfg, B, gemm_mode, data, W, b, steps, 2, sample_clocks=False)
+        nb = r["nbatches"]
+        out[f"c2_b{B}"] = {"value": round(cfg.N / (r["ms_step"] * 1e-3), 1), "e2e": round(cfg.N / (r["ms_e2e"] * 1e-3), 1),
+                           "ms_per_step": round(r["ms_step"], 3), "us_per_minibatch": round(1e3 * r["ms_step"] / nb, 2),
+                           "minibatches": nb, "launches_per_minibatch": round(r["launches"] / (steps * nb), 1),
+                           "steps": steps, "engine": r["engine"]}
+    # the largest byte mover at C2's shapes (18 KB of features per sample): the gather, against the HBM peak
+    ms, work = h.ctx.bench_kernel("gather0", cfg.N, cfg.nf * cfg.nhe, cfg.A, 4096, 10, True)
+    out["c2_b4096"]["K4_gather_frac_of_hbm"] = round(work / (ms * 1e-3) / 1e9 / peaks()["hbm"], 4)
+    return out
+
+
+def run_c5(h, args, gemm_mode):
+    """config C5: rollouts written to disk in the reference's format (trajectory.csv + one states/sample_i.bson per
+    transition: src/rollouts_to_disk.jl:23-132), bulk-loaded by the C++ replay loader, replicated in the device buffer
+    and run through the device update; every rank writes and replays its own shard.  Episodes have random_quad's shapes
+    (nf = 216, 4 actions per half-edge, <= 30 steps, Policy(216,128,2,4): test/random_quad.jl:43-49,61); the mesh
+    environments themselves need un-vendored packages."""
+    P, D = h.P, h.D
+    nf, nhe, apa, H, L = 216, 16, 4, 128, 2
+    on_disk, replayed = 2048, 131072
+    rng = np.random.default_rng(20260118 + 5 + 1000 * h.rank)
+    root = tempfile.mkdtemp(prefix=f"c5_rank{h.rank}_")
+    try:
+        return _run_c5_body(h, gemm_mode, root, rng, nf, nhe, apa, H, L, on_disk, replayed)
+    finally:
+        shutil.rmtree(root, ignore_errors=True)
+
+
+def _all_ranks_ok(h, ok):
+    """the disk phase is rank-local; the update phase is collective: go on only when every rank got there"""
+    if h.world == 1:
+        return ok
+    t = h.torch.tensor([1 if ok else 0], dtype=h.torch.int32)
+    h.dist.all_reduce(t, op=h.dist.ReduceOp.MIN)
+    return bool(t.item())
+
+
+def _run_c5_body(h, gemm_mode, root, rng, nf, nhe, apa, H, L, on_disk, replayed):
+    P, D = h.P, h.D
+    err = None
+    try:
+        t0 = time.perf_counter()
+        disk = P.DiskRollouts(root)
+        host = {"feat": [], "mask": [], "act": [], "prob": []}
+        while len(disk) < on_disk:
+            steps = int(min(rng.integers(1, 31), on_disk - len(disk)))
+            for s in range(steps):
+                vs = rng.integers(-3, 9, (nhe, nf)).astype(np.int64)               # Matrix{Int64}[nf, nhe]
+                am = np.repeat(np.where(rng.random(nhe // 4) < 0.25, -np.inf, 0.0), 4 * apa).astype(np.float32)
+                am[:4 * apa] = 0.0
+                a = int(rng.choice(np.flatnonzero(np.isfinite(am)))) + 1
+                p = float(np.float32(rng.uniform(0.05, 1.0)))
+                P.update_(disk, P.StateData(vs, am), p, a, float(rng.integers(-4, 5)), s == steps - 1)
+                host["feat"].append(vs.astype(np.int8)); host["mask"].append(am); host["act"].append(a); host["prob"].append(p)
+        P.write_returns_to_disk(disk, 1.0, h.ctx)
+        t_write = time.perf_counter() - t0
+        n_disk = len(disk)
+        t0 = time.perf_counter()
+        ds = P.DiskDataset(root)
+        buf, has_returns = ds.to_device(nf, nhe, apa, h.ctx, capacity=replayed)
+        h.ctx.sync()
+        t_load = time.perf_counter() - t0
+        got = buf.read(0, n_disk)
+        feat, mask = np.stack(host["feat"]), np.stack(host["mask"])
+        act, prob = np.array(host["act"], np.int64), np.array(host["prob"], np.float32)
+        bit_exact = bool(has_returns and np.array_equal(got["feat"], feat.astype(np.float32)) and np.array_equal(got["mask"], mask)
+                         and np.array_equal(got["selected_actions"], act)
+                         and np.allclose(got["selected_action_probabilities"], prob, rtol=1e-6))
+        ret = buf.rewards.copy()
+        while len(buf) + n_disk <= replayed:                                # replicate (returns are already final)
+            buf.append(feat, mask, prob, act, ret, np.zeros(n_disk, bool))
+        n = len(buf)
+    except Exception as e:   # noqa: BLE001
+        err = e
+    if not _all_ranks_ok(h, err is None):
+        raise RuntimeError(f"disk phase failed on a rank: {err}")
+    pol = P.Policy(nf, H, L, apa, h.ctx, gemm_mode=gemm_mode)
+    if h.use_p2p:
+        D.enable_p2p_gradients(pol)
+    opt = P.Optimiser(P.Adam(ETA))
+    B = max(1, 8192 // h.world)
+    dsd = P.construct_dataset(buf)
+    epochs = 3
+
+    def step(i):
+        P.ppo_train_(pol, opt, dsd, EPS, B, 1, W_ENT, seed=10 + i, out=None)
+
+    ms, _, _ = h.timed(step, epochs, 2, "c5 update")
+    out = {"on_disk_per_gpu": n_disk, "replayed_per_gpu": n, "replayed_total": n * h.world, "write_s": round(t_write, 2),
+           "load_s": round(t_load, 4), "load_transitions_per_s": round(n_disk / t_load, 1), "loaded_bit_exact": bit_exact,
+           "value": round(n * h.world / (ms * 1e-3), 1), "ms_per_epoch": round(ms, 3), "global_minibatch": B * h.world,
+           "policy": f"Policy({nf},{H},{L},{apa})", "engine": pol.gemm_mode}
+    pol.close(); buf.close()
+    return out
+
+
+def run_dp_parity(h, gemm_mode):
+    """N>1: one sharded epoch at C3's widths after the timed region, on the engine / gradient exchange the bench timed
+    (CUDA-graph replay included): replicas must be bit-identical, losses and post-Adam weights are compared with the CPU
+    restatement of the sharded scheme (global minibatch k = union of every rank's local minibatch k) on rank 0."""
+    P, S, D, dist = h.P, h.S, h.D, h.dist
+    from oracle import ppo_oracle as O
+    cfg = S.Config("c3-widths-dp-parity", 97, 8192, 64, 16, 4, 512, 3, 1024)
+    world, rank = h.world, h.rank
+    data = S.make_buffer(cfg)
+    W, b = S.make_weights(cfg)
+    old = S.rng_for(cfg, 7).uniform(0.05, 1.0, cfg.N).astype(np.float32)
+    bounds = D.shard_bounds_at_episode_ends(data["terminal"], world)
+    n_use = D.equalize_counts(bounds)
+    B = cfg.B // world
+    n_use -= n_use % B                       # full minibatches only: every rank replays the same CUDA graph
+    a0 = bounds[rank][0]
+    sl = slice(a0, a0 + n_use)
+    returns = O.compute_returns(data["reward"], data["terminal"], 1.0)      # shards are cut at episode ends
+    buf = P.DeviceRollouts(cfg.nf, cfg.nhe, cfg.apa, n_use, h.ctx)
+    buf.append(data["feat"][sl], data["mask"][sl], old[sl], data["action"][sl], returns[sl], data["terminal"][sl])
+    pol = P.Policy(cfg.nf, cfg.H, cfg.L, cfg.apa, h.ctx, weights=W, biases=b, gemm_mode=gemm_mode)
+    if h.use_p2p:
+        D.enable_p2p_gradients(pol)
+    losses = P.step_epoch_(pol, P.Adam(ETA), P.construct_dataset(buf), EPS, B, W_ENT, seed=D.local_seed(99, rank))
+    Wd, bd = pol.weights()
+    flat = np.concatenate([np.concatenate([w.ravel(), x.ravel()]) for w, x in zip(Wd, bd)])
+    gathered = [None] * world
+    dist.all_gather_object(gathered, (losses, flat.tobytes()))
+    pol.close(); buf.close()
+    if rank != 0:
+        return None
+    flats = [np.frombuffer(g[1], np.float32) for g in gathered]
+    identical = all(np.array_equal(flats[0], f) for f in flats[1:]) and all(g[0] == gathered[0][0] for g in gathered[1:])
+    opol = O.Policy(cfg.nf, cfg.H, cfg.L, cfg.apa)
+    opol.W, opol.b = [w.copy() for w in W], [x.copy() for x in b]
+    oopt = O.Adam(ETA)
+    perms = [O.feistel_permutation(n_use, D.local_seed(99, r)) + bounds[r][0] for r in range(world)]
+    ph, eh = [], []
+    for start in range(0, n_use, B):
+        idx = np.concatenate([pm[start:start + B] for pm in perms])
+        pl, ew = O.step_batch(opol, oopt, data["feat"][idx], data["mask"][idx], data["action"][idx], old[idx],
+                              returns[idx], EPS, W_ENT)
+        ph.append(pl); eh.append(ew)
+    want = (float(np.mean(ph)), float(np.mean(eh)))
+    loss_rel = max(abs(losses[0] - want[0]) / abs(want[0]), abs(losses[1] - want[1]) / abs(want[1]))
+    w_err = float(np.max(np.abs(flats[0] - opol.flat())))
+    disp = float(np.max(np.abs(opol.flat() - np.concatenate([np.concatenate([w.ravel(), x.ravel()]) for w, x in zip(W, b)]))))
+    ok = bool(identical and loss_rel <= 1e-5 and w_err <= 2e-5)
+    return {"ok": ok, "replicas_bit_identical": bool(identical), "loss_rel_err_vs_sharded_oracle": float(f"{loss_rel:.3g}"),
+            "weights_max_abs_err": float(f"{w_err:.3g}"), "weights_max_displacement": float(f"{disp:.3g}"),
+            "minibatches": n_use // B, "rows_per_rank": n_use, "mlp": "3x512", "tolerances": "loss 1e-5 rel, weights 2e-5 abs"}
+
+
+# ----------------------------------------------------------------------------------------------
 def run_ours(args):
     with _StdoutToStderr():
         line = _run_ours(args)
@@ -211,185 +629,89 @@ def run_ours(args):
 
 
 def _run_ours(args):
-    import torch
-    import torch.distributed as dist
-    import ppo_b200 as P
-    from ppo_b200 import synthetic as S
-    from ppo_b200 import distributed as D
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if world > 1:
-        dist.init_process_group("cpu:gloo,cuda:nccl", rank=rank, world_size=world)
-    torch.cuda.set_device(local_rank)
-    cfg = S.CONFIGS[args.config]
-    B_local = max(1, (args.batch or cfg.B) // world)
-    ctx = P.Context(local_rank)
-    if world > 1:
-        D.init_comm(ctx)
-    W, b = S.make_weights(cfg)
-    data = make_data(cfg, P, S, ctx, W, b, rank, cheap_old=args.profile)
-
+    h = Harness(args)
+    P, S = h.P, h.S
+    world, rank = h.world, h.rank
+    assert world == max(1, args.gpus) or world == 1, f"--gpus {args.gpus} but WORLD_SIZE={world}"
+    cfg, B_local, config = workload(_with_world(args, world))
+    feat_dtype = {"i8": np.int8, "f32": np.float32}[args.e2e_feat]
     gemm_mode = {"fp32": P.GEMM_FP32_SIMT, "tf32x3": P.GEMM_TF32X3_TC, "f16x3": P.GEMM_F16X3_TC}[args.gemm]
-    pol = P.Policy(cfg.nf, cfg.H, cfg.L, cfg.apa, ctx, weights=W, biases=b)
-    pol.set_gemm_mode(gemm_mode)
-    p2p = world > 1 and os.environ.get("PPO_B200_NO_P2P", "0") != "1" and D.enable_p2p_gradients(pol)
-    opt = P.Optimiser(P.Adam(ETA))
-    buf = P.DeviceRollouts(cfg.nf, cfg.nhe, cfg.apa, cfg.N, ctx)
-    stream = torch.cuda.ExternalStream(ctx.stream())
+    W, b = S.make_weights(cfg)
+    data = make_data(cfg, P, S, h.ctx, W, b, rank, feat_dtype, cheap_old=args.profile)
 
-    def fill():
-        buf.clear()
-        buf.append(data["feat"], data["mask"], data["old"], data["action"], data["reward"], data["terminal"])
-
-    def update(seed):
-        P.compute_state_value_(buf, GAMMA)
-        return P.ppo_train_(pol, opt, P.construct_dataset(buf), EPS, B_local, 1, W_ENT, seed=seed, out=None)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def timed(fn, steps, warmup, tag):
-        for i in range(warmup):
-            fn(i)
-        barrier()
-        sampler = ClockSampler(local_rank)
-        sampler.start()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        l0 = ctx.launch_count()
-        t0 = time.perf_counter()
-        e0.record(stream)
-        for i in range(steps):
-            fn(warmup + i)
-        e1.record(stream)
-        barrier()
-        wall = time.perf_counter() - t0
-        ms = e0.elapsed_time(e1)
-        clocks = sampler.stop()
-        launches = ctx.launch_count() - l0
-        if world > 1:
-            t = torch.tensor([ms], dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        log(f"[rank {rank}] {tag}: {ms / steps:.2f} ms/step (events), wall {1e3 * wall / steps:.2f} ms/step")
-        return ms / steps, clocks, launches
-
-    # ---- device-resident leg -------------------------------------------------------------------
-    fill()
-    buf.save_rewards()
-    last = {}
-
-    def resident_step(i):
-        buf.restore_rewards()
-        last["loss"] = update(1000 + i)
-
-    ms_step, clocks, launches = timed(resident_step, args.steps, args.warmup, "resident")
-    value = cfg.N * world / (ms_step * 1e-3)
+    main = run_update_legs(h, cfg, B_local, gemm_mode, data, W, b, args.steps, args.warmup, e2e=not args.profile)
+    value = cfg.N * world / (main["ms_step"] * 1e-3)
     if args.profile:
         line = None
         if rank == 0:
-            line = json.dumps({"profile_only": True, "value": value, "ms_per_step": ms_step, "gpu_launches": launches,
-                               "launches_total": ctx.launch_count()})
-        barrier()
-        pol.close(); buf.close(); ctx.close()
+            line = json.dumps({"profile_only": True, "value": value, "ms_per_step": main["ms_step"],
+                               "gpu_launches": main["launches"], "launches_total": h.ctx.launch_count()})
+        h.barrier()
+        h.ctx.close()
         return line
+    e2e = {"value": cfg.N * world / (main["ms_e2e"] * 1e-3), "unit": UNIT,
+           "h2d_bytes_per_step": cfg.N * host_bytes_per_transition(cfg, feat_dtype),
+           "d2h_bytes_per_step": 16 * main["nbatches"], "ms_per_step": main["ms_e2e"], "steps": args.steps}
+    del data
 
-    # ---- end-to-end leg: host buffers in, losses out ----------------------------------------------
-    def e2e_step(i):
-        fill()
-        last["loss"] = update(2000 + i)
+    extras, errors = {}, {}
 
-    e2e_steps = max(1, min(args.steps, 3))
-    ms_e2e, _, _ = timed(e2e_step, e2e_steps, 1, "e2e")
-    h2d = cfg.N * (4 * cfg.nf * cfg.nhe + 4 * cfg.A + 8 + 4 + 4 + 1)
-    d2h = 16 * ((cfg.N + B_local - 1) // B_local)
-    e2e = {"value": cfg.N * world / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
-           "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e}
+    def guarded(name, fn):
+        try:
+            return fn()
+        except Exception as e:   # noqa: BLE001  (an extra leg must never cost the headline line)
+            errors[name] = f"{type(e).__name__}: {e}"[:300]
+            log(f"[rank {rank}] extra leg {name} failed: {errors[name]}")
+            return None
+
+    roofline, kernels, cpu = None, None, None
+    if not args.no_extras:
+        if rank == 0:
+            res = guarded("kernels", lambda: kernel_rooflines(h, cfg, B_local, args.gemm))
+            if res:
+                roofline, kernels = res
+                if world == 1:
+                    tr = guarded("traffic", lambda: ncu_traffic_probe(B_local * cfg.nhe, cfg.H, {"fp32": "gemm_fwd", "tf32x3": "tc1_fwd", "f16x3": "tc3_fwd"}[args.gemm]))
+                    if tr:
+                        roofline["traffic"], roofline["traffic_source"] = tr
+            if world == 1:
+                # the CPU baseline is timed at N = 1 only (torchrun pins OMP_NUM_THREADS=1 and the ranks share the host)
+                cpu = guarded("cpu_baseline", lambda: cpu_baseline(cfg))
+                c2 = guarded("c2", lambda: run_c2(h, args, gemm_mode))
+                if c2:
+                    extras.update(c2)
+        c5 = guarded("c5", lambda: run_c5(h, args, gemm_mode))
+        if c5:
+            extras["c5"] = c5
+    dp_parity = guarded("dp_parity", lambda: run_dp_parity(h, gemm_mode)) if world > 1 else None
 
     out = None
     if rank == 0:
-        pk = peaks()
-        # ---- per-kernel rooflines, measured live with CUDA events on the library's stream ----------
-        kernels = {}
-        M = B_local * cfg.nhe
-
-        def hbm(name, which, n, a=0, b_=0, c=0, iters=10):
-            ms, work = ctx.bench_kernel(which, n, a, b_, c, iters, True)
-            gbs = work / (ms * 1e-3) / 1e9
-            kernels[name] = {"bound": "hbm", "achieved": round(gbs, 1), "peak": pk["hbm"], "unit": "GB/s",
-                             "frac": round(gbs / pk["hbm"], 4), "ms": round(ms, 4), "bytes": work}
-
-        hbm("K1_scan_namedN", "scan", cfg.N, 15)
-        hbm("K1_scan_64M", "scan", 64 * 1024 * 1024, 15, iters=5)
-        hbm("K1K2_scan_64M_with_norm_stats", "scan_norm", 64 * 1024 * 1024, 15, iters=5)
-        hbm("K3_shuffle", "shuffle", cfg.N)
-        hbm("K4_gather_ldg", "gather0", cfg.N, cfg.nf * cfg.nhe, cfg.A, B_local)
-        hbm("K4_gather_bulk", "gather1", cfg.N, cfg.nf * cfg.nhe, cfg.A, B_local)
-        hbm("K6_loss_namedB", "loss", B_local, cfg.A)
-        hbm("K6_loss_1M", "loss", 1 << 20, cfg.A, iters=5)
-        hp = "head16" if args.gemm == "f16x3" else "head"     # the fp16-split engine has its own head kernels
-        hbm("K5_head_fwd", hp + "_fwd", M, cfg.H, cfg.apa, iters=5)
-        hbm("K7_head_bwd", hp + "_bwd", M, cfg.H, cfg.apa, iters=5)
-        hbm("K1_scan_64M_longepisodes", "scan", 64 * 1024 * 1024, 1 << 30, 1, iters=3)
-        hbm("K8_adam", "adam", cfg.num_params)
-        gname = {"fp32": "gemm", "tf32x3": "tc1", "f16x3": "tc3"}[args.gemm]
-        dom = {}
-        for kind in ("fwd", "dgrad", "wgrad"):
-            ms, flops = ctx.bench_kernel(f"{gname}_{kind}", M, cfg.H, cfg.H, 0, 3, True)
-            tf = flops / (ms * 1e-3) / 1e12
-            dom[kind] = {"ms": round(ms, 4), "tflops_fp32_equiv": round(tf, 2)}
-            kernels[f"K5K7_gemm_{kind}_{cfg.H}x{cfg.H}"] = {
-                "bound": "tensor", "achieved": round(tf, 2), "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
-                "frac": round(tf / pk["bf16_sustained"], 4), "ms": round(ms, 4), "flops": flops}
-        # the dominant kernel of the step: the hidden-layer forward/dgrad GEMM kernel (tc_gemm_kk_kernel<256>, 50 % of
-        # the step in the ncu launch list).  `achieved` counts ALGORITHMIC flops (2 M K N of the fp32 GEMM it
-        # replaces); the 3-pass error-compensated scheme issues 3x as many tf32 tensor flops, and tf32 runs at half the
-        # bf16 rate, so the ceiling of this scheme is peak / 6.
-        fwd = dom["fwd"]
-        ach = fwd["tflops_fp32_equiv"]
-        passes = 3 if args.gemm in ("tf32x3", "f16x3") else 1
-        # ceiling of the 3-pass split: tf32 runs at half the bf16/fp16 rate (peak / 6); fp16 at the full rate (peak / 3)
-        ceiling = pk["bf16_sustained"] / (6.0 if args.gemm == "tf32x3" else 3.0)
-        kname = {"tf32x3": "tc_gemm_kk_kernel<256>", "f16x3": "f16_gemm_kk_kernel<256, CTA pair>", "fp32": "sgemm_kernel"}[args.gemm]
-        roofline = {"bound": "tensor", "achieved": ach, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
-                    "frac": round(ach / pk["bf16_sustained"], 4),
-                    "traffic": ({"tf32x3": 8.65e9, "f16x3": 4.34e9}.get(args.gemm)
-                                if (M == 1 << 20 and cfg.H == 512) else None),
-                    "kernel": kname + f" (hidden Dense forward, M={M}, K=N={cfg.H})",
-                    "ms_per_launch": fwd["ms"],
-                    "peak_source": pk["src"] + " bf16 sustained (MEASURED_PEAKS.json; kernel timed inside a long step)",
-                    "tensor_flops_issued_tflops": round(ach * passes, 2),
-                    "frac_of_3pass_ceiling": round(ach / ceiling, 4) if passes == 3 else None,
-                    "traffic_source": {"tf32x3": "ncu --set full, profiles/r01_ncu_summary.md (dram read 4.38 GB + write 4.27 GB per launch)",
-                                       "f16x3": "ncu --set full, profiles/r01_f16_ncu.md (dram read 2.17 GB + write 2.18 GB per launch "
-                                                "= the algorithmic bytes of the fp16 hi/lo pairs)"}.get(args.gemm),
-                    "detail": dom}
-        # the CPU baseline is timed at N = 1 only (torchrun pins OMP_NUM_THREADS=1 and the ranks share the host)
-        cpu = cpu_baseline(cfg, data, W, b) if world == 1 else None
+        if roofline is not None:
+            # step level: algorithmic MLP flops per step against the measured sustained tensor peak
+            pk = peaks()
+            step_tf = cfg.flops_per_sample() * cfg.N / (main["ms_step"] * 1e-3) / 1e12
+            roofline["step"] = {"algorithmic_tflops": round(step_tf, 1), "frac_of_peak": round(step_tf / pk["bf16_sustained"], 4),
+                                "frac_of_3pass_ceiling": round(3 * step_tf / pk["bf16_sustained"], 4)}
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": main["ms_step"], "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None, "dtype": {"fp32": "f32", "tf32x3": "tf32x3", "f16x3": "f16x3"}[args.gemm],
-            "data": "synthetic",
-            "config": {"workload": cfg.name + (f" x{world} shards" if world > 1 else ""),
-                       "transitions_per_gpu": cfg.N, "minibatch_rows_per_gpu": B_local,
-                       "global_minibatch": B_local * world, "mlp": f"{cfg.L}x{cfg.H}", "nf": cfg.nf, "nhe": cfg.nhe,
-                       "actions_per_state": cfg.A, "epochs_per_step": 1, "gemm_engine": args.gemm,
-                       "parallelism": f"dp{world}" if world > 1 else "single",
-                       "grad_exchange": ("nvlink peer memory, fused into the Adam kernel" if p2p else "nccl all-reduce") if world > 1 else None,
-                       "l2": "step inputs (4.6 GB) exceed L2; per-kernel timings flush L2 between launches (write 256 MB, then read 256 MB so that no dirty flush lines are written back inside the timed kernel)"},
-            "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu, "e2e": e2e,
-            "gpu_launches": launches, "clocks": clocks,
-            "loss_last_step": [float(last["loss"][0][0]), float(last["loss"][1][0])],
+            "data": "synthetic", "kernels": kernels, "config": config, "cpu_baseline": cpu,
+            "gpu_launches": main["launches"], "clocks": main["clocks"], "loss_last_step": main["loss"],
+            "roofline": roofline, "e2e": e2e, "errors": errors or None, "configs": extras or None, "dp_parity": dp_parity,
         }
-    barrier()
-    pol.close(); buf.close(); ctx.close()
+    h.barrier()
+    h.ctx.close()
     if world > 1:
-        dist.destroy_process_group()
+        h.dist.destroy_process_group()
     return json.dumps(out) if out is not None else None
+
+
+def _with_world(args, world):
+    a = argparse.Namespace(**vars(args))
+    a.gpus = world
+    return a
 
 
 def run_reference(args):
@@ -399,36 +721,29 @@ def run_reference(args):
         return
     import torch
     import ppo_b200  # noqa: F401  (package only for the synthetic generator; no CUDA call is made)
-    from ppo_b200 import synthetic as S
-    from oracle import ppo_oracle as O
-    cfg = S.CONFIGS[args.config]
-    n = min(cfg.N, 131072)                      # bounded sample of the buffer
-    import dataclasses
-    small = dataclasses.replace(cfg, N=n)
-    data = S.make_buffer(small)
-    W, b = S.make_weights(cfg)
-    data["old"] = np.full(n, 1.0 / cfg.A, np.float32)
+    cfg, B_local, config = workload(args)
+    n = min(cfg.N, 65536)                      # bounded sample of the buffer
+    data, W, b = cpu_sample_data(cfg, n)
     limiter, threads = host_blas_threads(want_all=True)      # all host cores, also under torchrun (OMP_NUM_THREADS=1)
     torch.set_num_threads(threads)
-    rows = min(cfg.B, 2048)
-    t = cpu_reference_step(cfg, data, W, b, rows, threads)
+    rows = min(cfg.B, 2048, n)
+    t = cpu_reference_step(cfg, data, W, b, rows)
     rows = int(min(cfg.B, n, max(rows, rows / t * 8.0)))   # ~8 s of CPU work per step
     times = []
     for i in range(args.warmup + args.steps):
         if i < args.warmup and i > 0:
             continue                                         # one warm-up pass is enough on the CPU
-        t = cpu_reference_step(cfg, data, W, b, rows, threads)
+        t = cpu_reference_step(cfg, data, W, b, rows)
         if i >= args.warmup:
             times.append(t)
     t = float(np.mean(times))
     v = rows / t
     out = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-           "warmup": args.warmup, "ms_per_step": 1e3 * t, "higher_is_better": True, "scaling": "weak",
-           "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-           "config": {"workload": cfg.name, "mlp": f"{cfg.L}x{cfg.H}", "sample_rows_per_step": rows},
+           "warmup": args.warmup, "ms_per_step": 1e3 * t, "higher_is_better": True, "scaling": args.scaling,
+           "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
            "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
-                            "sample": f"{rows} transitions per step of config {cfg.name} (restated CPU path; Julia is "
-                                      "not installable in this image)"},
+                            "sample": f"each step = one minibatch of {rows} transitions out of the first {n} of the workload "
+                                      f"(restated CPU path, per-sample throughput; Julia is not installable in this image)"},
            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out), flush=True)
 
@@ -443,9 +758,14 @@ def main():
     ap.add_argument("--profile", action="store_true",
                     help="only the warm-up + timed resident steps (for ncu launch lists): no data-generation forward, "
                          "no per-kernel hooks, no CPU baseline")
+    ap.add_argument("--no-extras", action="store_true", help="headline + e2e only (no per-kernel hooks, C2 / C5 legs)")
     ap.add_argument("--config", default="c3")
     ap.add_argument("--batch", type=int, default=0,
                     help="override the global minibatch size (profiling the small-minibatch regime of the N-GPU runs on one GPU)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: a C3-sized shard per GPU (default; = config C4 at N=8); strong: config C4 as written, "
+                         "8 388 608 transitions in total at any N")
+    ap.add_argument("--e2e-feat", default="i8", choices=["i8", "f32"], help="dtype of the host-side features of the e2e leg")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

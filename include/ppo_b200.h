@@ -89,6 +89,15 @@ int ppo_buffer_append(ppo_buf* buf, int64_t n, const float* feat, const float* m
 int ppo_buffer_append_i64(ppo_buf* buf, int64_t n, const int64_t* feat, const float* mask,
                           const int64_t* action, const float* old_prob, const float* reward,
                           const uint8_t* terminal);
+/* same, features given as Int8 / Int16: exact for the small-integer scores a quad-game state holds (vertex score,
+ * degree, 0 for missing: test/quad_game_utilities.jl:35-37, 50-56) at a quarter / half of the Float32 host->device
+ * bytes; widened to Float32 on the device.  The caller narrows (and range-checks) its Matrix{Int64}. */
+int ppo_buffer_append_i8(ppo_buf* buf, int64_t n, const int8_t* feat, const float* mask,
+                         const int64_t* action, const float* old_prob, const float* reward,
+                         const uint8_t* terminal);
+int ppo_buffer_append_i16(ppo_buf* buf, int64_t n, const int16_t* feat, const float* mask,
+                          const int64_t* action, const float* old_prob, const float* reward,
+                          const uint8_t* terminal);
 /* Base.length, :40-48 */
 int64_t ppo_buffer_length(ppo_buf* buf);
 int ppo_buffer_clear(ppo_buf* buf);

@@ -11,6 +11,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <type_traits>
 #include <new>
 
 #include "common.cuh"
@@ -274,27 +275,66 @@ int read_batch_to_host(ppo_ctx* ctx, const ppo_batch& bt, int64_t count, int fea
     return PPO_OK;
 }
 
-int append_common(ppo_buf* buf, int64_t n, const void* feat, bool feat_i64, const float* mask, const int64_t* action,
+// BufferRollouts grows without bound (push!, src/rollout_buffer.jl:24-38); the device buffer's capacity is an initial
+// reservation that grows geometrically: new arrays, device-to-device copies of the n live transitions, old arrays freed
+int grow_buffer(ppo_buf* buf, int64_t need) {
+    ppo_ctx* ctx = buf->ctx;
+    int64_t cap = std::max<int64_t>(need, buf->cap + buf->cap / 2 + 1024);
+    PPO_REQUIRE(cap < ((int64_t)1 << 31), "append: %lld transitions exceed the buffer's index range", (long long)need);
+    const int64_t fe = (int64_t)buf->nf * buf->nhe;
+    const int64_t cap16 = round_up(cap, SCAN_TILE), old16 = round_up(buf->cap, SCAN_TILE);
+    PPO_CUDA(cudaStreamSynchronize(ctx->stream));
+    auto move = [&](auto*& arr, size_t new_count, size_t live) -> int {
+        using T = std::remove_reference_t<decltype(*arr)>;
+        T* fresh = nullptr;
+        PPO_TRY(dev_alloc(&fresh, new_count));
+        if (arr != nullptr && live > 0)
+            PPO_CUDA(cudaMemcpyAsync(fresh, arr, live * sizeof(T), cudaMemcpyDeviceToDevice, ctx->stream));
+        PPO_CUDA(cudaStreamSynchronize(ctx->stream));
+        dev_free(arr);
+        arr = fresh;
+        return PPO_OK;
+    };
+    const size_t n = (size_t)buf->n;
+    PPO_TRY(move(buf->feat, (size_t)cap * fe, n * fe));
+    PPO_TRY(move(buf->mask, (size_t)cap * buf->A, n * buf->A));
+    PPO_TRY(move(buf->action, (size_t)cap, n));
+    PPO_TRY(move(buf->old_prob, (size_t)cap, n));
+    PPO_TRY(move(buf->reward, (size_t)cap16, std::min<size_t>(n, (size_t)old16)));
+    PPO_TRY(move(buf->reward_alt, (size_t)cap16, 0));
+    PPO_TRY(move(buf->terminal, (size_t)cap16, n));
+    PPO_TRY(move(buf->perm, (size_t)cap, (size_t)buf->perm_len));
+    PPO_TRY(move(buf->d_tile_stats, (size_t)2 * SCAN_STATS_PER_TILE * ceil_div(cap, SCAN_TILE), 0));
+    if (buf->reward_saved) PPO_TRY(move(buf->reward_saved, (size_t)cap, (size_t)buf->saved_n));
+    buf->stats_valid = false;
+    buf->cap = cap;
+    return PPO_OK;
+}
+
+// feat_bytes: element size of the host features: 4 = Float32 (copied as is), 8 = Int64, 1 / 2 = Int8 / Int16 (staged in
+// scratch, widened to Float32 on the device; exact)
+int append_common(ppo_buf* buf, int64_t n, const void* feat, int feat_bytes, const float* mask, const int64_t* action,
                   const float* old_prob, const float* reward, const uint8_t* terminal) {
     ppo_ctx* ctx = buf->ctx;
     PPO_TRY(use(ctx));
     PPO_REQUIRE(n >= 0, "append: n < 0");
-    PPO_REQUIRE(buf->n + n <= buf->cap, "append: capacity exceeded (%lld + %lld > %lld)", (long long)buf->n,
-                (long long)n, (long long)buf->cap);
     if (n == 0) return PPO_OK;
     PPO_REQUIRE(feat && mask && action && old_prob && reward && terminal, "append: null input");
+    if (buf->n + n > buf->cap) PPO_TRY(grow_buffer(buf, buf->n + n));
     const int64_t fe = (int64_t)buf->nf * buf->nhe;
     const int64_t off = buf->n;
-    size_t scratch = (size_t)n * 8 + 64;
-    if (feat_i64) scratch += (size_t)n * fe * 8;
+    const size_t act_bytes = (size_t)round_up(n * 8, 64);
+    size_t scratch = 64 + act_bytes;
+    if (feat_bytes != 4) scratch += (size_t)n * fe * feat_bytes;
     PPO_TRY(ensure_scratch(ctx, scratch));
     int* d_bad = (int*)ctx->d_scratch;
     int64_t* d_act = (int64_t*)((char*)ctx->d_scratch + 64);
     PPO_CUDA(cudaMemsetAsync(d_bad, 0, sizeof(int), ctx->stream));
-    if (feat_i64) {
-        int64_t* d_f = d_act + n;
-        PPO_TRY(h2d(ctx, d_f, feat, (size_t)n * fe * 8));
-        PPO_TRY(launch_i64_to_f32(ctx, d_f, buf->feat + off * fe, n * fe));
+    if (feat_bytes != 4) {
+        void* d_f = (char*)ctx->d_scratch + 64 + act_bytes;
+        PPO_TRY(h2d(ctx, d_f, feat, (size_t)n * fe * feat_bytes));
+        if (feat_bytes == 8) PPO_TRY(launch_i64_to_f32(ctx, (const int64_t*)d_f, buf->feat + off * fe, n * fe));
+        else PPO_TRY(launch_narrow_to_f32(ctx, d_f, feat_bytes, buf->feat + off * fe, n * fe));
     } else {
         PPO_TRY(h2d(ctx, buf->feat + off * fe, feat, (size_t)n * fe * 4));
     }
@@ -374,15 +414,23 @@ int ppo_ctx_create(int device, ppo_ctx** out) {
     PPO_CUDA(cudaGetDeviceProperties(&prop, device));
     c->num_sms = prop.multiProcessorCount;
     PPO_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-    PPO_CUDA(cudaMallocHost((void**)&c->h_pinned, sizeof(double) * ppo_ctx::PINNED_DOUBLES));
+    c->pinned_doubles = 1 << 12;
+    PPO_CUDA(cudaMallocHost((void**)&c->h_pinned, sizeof(double) * (size_t)c->pinned_doubles));
     PPO_CUDA(cudaMalloc((void**)&c->d_step, sizeof(int)));
     PPO_CUDA(cudaMemset(c->d_step, 0, sizeof(int)));
     *out = c;
     return PPO_OK;
 }
 
+// children call this from their destroy functions (after releasing their own device memory)
+static void ctx_release_child(ppo_ctx* ctx) {
+    if (ctx == nullptr) return;
+    if (--ctx->children <= 0 && ctx->dead) { ctx->dead = false; ppo_ctx_destroy(ctx); }
+}
+
 int ppo_ctx_destroy(ppo_ctx* ctx) {
     if (!ctx) return PPO_OK;
+    if (ctx->children > 0) { ctx->dead = true; return PPO_OK; }      // released by the last child (see ppo_ctx::children)
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     nccl_destroy(ctx);
@@ -443,6 +491,7 @@ int ppo_buffer_create(ppo_ctx* ctx, int64_t capacity, int nf, int nhe, int apa, 
     ppo_buf* b = new (std::nothrow) ppo_buf();
     if (!b) { set_error("out of host memory"); return PPO_ERR_NOMEM; }
     b->ctx = ctx; b->cap = capacity; b->nf = nf; b->nhe = nhe; b->apa = apa; b->A = nhe * apa;
+    ctx->children += 1;
     const int64_t cap16 = round_up(capacity, SCAN_TILE);   // scan reads whole 16-item chunks only when in range
     int s = PPO_OK;
     if ((s = dev_alloc(&b->feat, (size_t)capacity * nf * nhe)) != PPO_OK ||
@@ -469,20 +518,34 @@ int ppo_buffer_destroy(ppo_buf* b) {
     dev_free(b->feat); dev_free(b->mask); dev_free(b->action); dev_free(b->old_prob); dev_free(b->reward);
     dev_free(b->terminal); dev_free(b->perm); dev_free(b->reward_saved); dev_free(b->reward_alt); dev_free(b->d_norm); dev_free(b->d_tile_stats);
     free_batch(b->batch);
+    ppo_ctx* ctx = b->ctx;
     delete b;
+    ctx_release_child(ctx);
     return PPO_OK;
 }
 
 int ppo_buffer_append(ppo_buf* buf, int64_t n, const float* feat, const float* mask, const int64_t* action,
                       const float* old_prob, const float* reward, const uint8_t* terminal) {
     PPO_REQUIRE(buf != nullptr, "null buffer");
-    return append_common(buf, n, feat, false, mask, action, old_prob, reward, terminal);
+    return append_common(buf, n, feat, 4, mask, action, old_prob, reward, terminal);
 }
 
 int ppo_buffer_append_i64(ppo_buf* buf, int64_t n, const int64_t* feat, const float* mask, const int64_t* action,
                           const float* old_prob, const float* reward, const uint8_t* terminal) {
     PPO_REQUIRE(buf != nullptr, "null buffer");
-    return append_common(buf, n, feat, true, mask, action, old_prob, reward, terminal);
+    return append_common(buf, n, feat, 8, mask, action, old_prob, reward, terminal);
+}
+
+int ppo_buffer_append_i8(ppo_buf* buf, int64_t n, const int8_t* feat, const float* mask, const int64_t* action,
+                         const float* old_prob, const float* reward, const uint8_t* terminal) {
+    PPO_REQUIRE(buf != nullptr, "null buffer");
+    return append_common(buf, n, feat, 1, mask, action, old_prob, reward, terminal);
+}
+
+int ppo_buffer_append_i16(ppo_buf* buf, int64_t n, const int16_t* feat, const float* mask, const int64_t* action,
+                          const float* old_prob, const float* reward, const uint8_t* terminal) {
+    PPO_REQUIRE(buf != nullptr, "null buffer");
+    return append_common(buf, n, feat, 2, mask, action, old_prob, reward, terminal);
 }
 
 int64_t ppo_buffer_length(ppo_buf* buf) { return buf ? buf->n : -1; }
@@ -734,6 +797,7 @@ int ppo_policy_create(ppo_ctx* ctx, int n_layers, const int* dims, const float* 
     ppo_policy* p = new (std::nothrow) ppo_policy();
     if (!p) { set_error("out of host memory"); return PPO_ERR_NOMEM; }
     p->ctx = ctx; p->L = n_layers; p->slope = leaky_slope;
+    ctx->children += 1;
     p->dims.assign(dims, dims + n_layers + 1);
     int64_t off = 0;
     for (int l = 0; l < n_layers; ++l) {
@@ -772,7 +836,9 @@ int ppo_policy_destroy(ppo_policy* p) {
     p2p_destroy(p);
     dev_free(p->params); dev_free(p->grads); dev_free(p->d_loss_partials); dev_free(p->d_loss_hist);
     free_batch(p->hbatch);
+    ppo_ctx* ctx = p->ctx;
     delete p;
+    ctx_release_child(ctx);
     return PPO_OK;
 }
 
@@ -931,6 +997,7 @@ int ppo_adam_create(ppo_policy* p, double eta, double beta1, double beta2, doubl
     ppo_opt* o = new (std::nothrow) ppo_opt();
     if (!o) { set_error("out of host memory"); return PPO_ERR_NOMEM; }
     o->ctx = ctx; o->policy = p; o->eta = eta; o->beta1 = beta1; o->beta2 = beta2; o->eps = eps;
+    ctx->children += 1;
     int s;
     if ((s = dev_alloc(&o->m, (size_t)p->P)) != PPO_OK || (s = dev_alloc(&o->v, (size_t)p->P)) != PPO_OK ||
         (s = dev_alloc(&o->d_bp, 2)) != PPO_OK) {
@@ -951,7 +1018,9 @@ int ppo_adam_destroy(ppo_opt* o) {
     cudaSetDevice(o->ctx->device);
     cudaStreamSynchronize(o->ctx->stream);
     dev_free(o->m); dev_free(o->v); dev_free(o->d_bp);
+    ppo_ctx* ctx = o->ctx;
     delete o;
+    ctx_release_child(ctx);
     return PPO_OK;
 }
 
@@ -1088,8 +1157,15 @@ int ppo_step_epoch(ppo_policy* p, ppo_opt* opt, ppo_buf* buf, double epsilon, in
         return PPO_ERR_STATE;
     }
     const int64_t nbatches = ceil_div(num_data, batch_size);
-    PPO_REQUIRE(nbatches + 1 <= ppo_ctx::PINNED_DOUBLES / 2, "step_epoch: too many minibatches (%lld)",
-                (long long)nbatches);
+    if (2 * nbatches > ctx->pinned_doubles) {        // the loss history is read back through pinned staging: grow it on demand
+        PPO_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (ctx->h_pinned) PPO_CUDA(cudaFreeHost(ctx->h_pinned));
+        ctx->h_pinned = nullptr;
+        ctx->pinned_doubles = 0;
+        const int64_t want = round_up(2 * nbatches, 4096);
+        PPO_CUDA(cudaMallocHost((void**)&ctx->h_pinned, sizeof(double) * (size_t)want));
+        ctx->pinned_doubles = want;
+    }
     const bool dp = ctx->nccl_comm != nullptr && ctx->nranks > 1;
     // global row count of every minibatch (local count when single-GPU)
     std::vector<double> counts((size_t)nbatches + 1);

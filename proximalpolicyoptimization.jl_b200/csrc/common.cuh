@@ -67,7 +67,12 @@ struct ppo_ctx {
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     bool comm_pending = false;
     bool p2p_grads = false;          // a policy of this context exchanges gradients over peer memory (dp_p2p.cu)
-    static constexpr int PINNED_DOUBLES = 1 << 16;
+    // Destruction order: garbage-collected bindings (Julia finalizers at exit) may destroy the context before the
+    // buffers / policies / optimisers that live on it.  ppo_ctx_destroy only marks the context dead while children are
+    // alive; the last child's destroy call then releases it.
+    int children = 0;
+    bool dead = false;
+    int64_t pinned_doubles = 0;      // capacity of h_pinned (grown on demand)
 };
 
 // minibatch staging area (output of the K4 gather; input of the MLP / loss)
@@ -186,6 +191,7 @@ int launch_convert_actions_in(ppo_ctx* ctx, const int64_t* a1, int* a0, int64_t 
 int launch_convert_actions_out(ppo_ctx* ctx, const int* a0, int64_t* a1, int64_t n);
 int launch_linear_index_in(ppo_ctx* ctx, const int64_t* lin1, int* a0, int64_t n, int A, int* d_bad);
 int launch_i64_to_f32(ppo_ctx* ctx, const int64_t* src, float* dst, int64_t n);
+int launch_narrow_to_f32(ppo_ctx* ctx, const void* src, int elem_bytes /* 1: int8, 2: int16 */, float* dst, int64_t n);
 int launch_normalize_bool(ppo_ctx* ctx, uint8_t* t, int64_t n);
 int launch_step_advance(ppo_ctx* ctx, int* d_step);
 

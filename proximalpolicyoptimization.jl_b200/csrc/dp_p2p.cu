@@ -16,7 +16,7 @@
 // The exchange buffer is double buffered by the parity of the epoch: a rank overwrites xchg[e & 1] at epoch e + 2, i.e.
 // after its Adam of epoch e + 1 saw every peer's flag e + 2, and a peer raises that flag only after its own Adam of
 // epoch e (the reader of xchg[e & 1]) has finished — no second handshake is needed.  One process per GPU, one node.
-// A spin that exceeds ~4 s (a peer died) raises an error flag instead of hanging the GPU.
+// A spin that exceeds ~4 s (a peer died) raises an error flag instead of hanging the GPU, and the update is skipped.
 #include <string.h>
 
 #include <algorithm>
@@ -76,15 +76,22 @@ p2p_adam_kernel(float* __restrict__ x, float* __restrict__ m, float* __restrict_
                 double eps, const double* __restrict__ bp, const float* const* __restrict__ peer_xchg, int64_t Ppad,
                 const unsigned* flags, unsigned* state, int nranks, float* __restrict__ grads_out) {
     const unsigned epoch = state[0];
+    // A peer that never publishes (it died) must not hang the GPU: after ~4 s the block raises the sticky error word and
+    // SKIPS its share of the update (no sum of stale exchange buffers ever reaches the weights or the moments); every later
+    // launch sees the word and skips at once, and the host turns it into an error before it reads the losses.
+    __shared__ int s_abort;
     if (threadIdx.x == 0) {
+        int abort_ = __ldcg(state + 2) != 0u;
         const long long t0 = clock64();
-        for (int q = 0; q < nranks; ++q)
+        for (int q = 0; q < nranks && !abort_; ++q)
             while (ld_acquire_sys(flags + q) < epoch + 1u) {
-                if (clock64() - t0 > 8000000000ll) { state[2] = 1u; break; }     // ~4 s: a peer is gone
+                if (clock64() - t0 > 8000000000ll) { state[2] = 1u; abort_ = 1; break; }
                 __nanosleep(64);
             }
+        s_abort = abort_;
     }
     __syncthreads();
+    if (s_abort) return;
     const size_t off = (size_t)(epoch & 1u) * Ppad;
     const double b1p = bp[0], b2p = bp[1];
     const double om1 = 1.0 - b1, om2 = 1.0 - b2;

@@ -243,6 +243,27 @@ i64_to_f32_kernel(const int64_t* __restrict__ s, float* __restrict__ d, int64_t 
         d[i] = (float)s[i];
 }
 
+// narrow integer features -> Float32 (exact), 16 elements per thread: 16 / 32 bytes in, 64 bytes out
+template <typename T>
+__global__ void __launch_bounds__(256)
+narrow_to_f32_kernel(const T* __restrict__ s, float* __restrict__ d, int64_t n) {
+    const int64_t n16 = n >> 4;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (int64_t)gridDim.x * blockDim.x) {
+        T v[16];
+        if (sizeof(T) == 1) {
+            *reinterpret_cast<uint4*>(v) = __ldcs(reinterpret_cast<const uint4*>(s) + i);
+        } else {
+            reinterpret_cast<uint4*>(v)[0] = __ldcs(reinterpret_cast<const uint4*>(s) + 2 * i);
+            reinterpret_cast<uint4*>(v)[1] = __ldcs(reinterpret_cast<const uint4*>(s) + 2 * i + 1);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            reinterpret_cast<float4*>(d)[4 * i + q] = make_float4((float)v[4 * q], (float)v[4 * q + 1], (float)v[4 * q + 2], (float)v[4 * q + 3]);
+    }
+    const int64_t tail = (n16 << 4) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (blockIdx.x == 0 && tail < n) d[tail] = (float)s[tail];      // < 16 leftover elements
+}
+
 inline unsigned grid_for(ppo_ctx* ctx, int64_t n, int per_block, int waves = 8) {
     int64_t want = ceil_div(n, per_block);
     int64_t cap = (int64_t)ctx->num_sms * waves;
@@ -340,6 +361,17 @@ int launch_normalize_bool(ppo_ctx* ctx, uint8_t* t, int64_t n) {
 int launch_i64_to_f32(ppo_ctx* ctx, const int64_t* src, float* dst, int64_t n) {
     if (n <= 0) return PPO_OK;
     i64_to_f32_kernel<<<grid_for(ctx, n, 256), 256, 0, ctx->stream>>>(src, dst, n);
+    ctx->launches += 1;
+    PPO_CUDA(cudaGetLastError());
+    return PPO_OK;
+}
+
+int launch_narrow_to_f32(ppo_ctx* ctx, const void* src, int elem_bytes, float* dst, int64_t n) {
+    if (n <= 0) return PPO_OK;
+    PPO_REQUIRE(((uintptr_t)src % 16 == 0) && ((uintptr_t)dst % 16 == 0), "narrow_to_f32: unaligned buffers");
+    const unsigned grid = grid_for(ctx, n / 16 + 1, 256, 16);
+    if (elem_bytes == 1) narrow_to_f32_kernel<int8_t><<<grid, 256, 0, ctx->stream>>>((const int8_t*)src, dst, n);
+    else narrow_to_f32_kernel<int16_t><<<grid, 256, 0, ctx->stream>>>((const int16_t*)src, dst, n);
     ctx->launches += 1;
     PPO_CUDA(cudaGetLastError());
     return PPO_OK;

@@ -22,6 +22,9 @@ end
 last_error() = unsafe_string(ccall((:ppo_last_error, lib), Cstring, ()))
 check(status::Cint) = status == 0 ? nothing : throw(PPOError(status, last_error()))
 
+# Destruction order: the library reference-counts the children of a context (buffers, policies, optimisers), so the
+# finalizers below may run in any order (ppo_ctx_destroy on a context with live children only marks it; the last child's
+# destroy call releases it).
 # ---- context -------------------------------------------------------------------------------------
 mutable struct Context
     h::Ptr{Cvoid}
@@ -45,22 +48,35 @@ mutable struct DeviceRollouts
     act::Vector{Int64}; rew::Vector{Float32}; term::Vector{UInt8}
 end
 
-function DeviceRollouts(ctx::Context, nf, nhe, apa, capacity)
+# `capacity` is an initial reservation (the device arrays grow like the reference's push!-grown vectors)
+function DeviceRollouts(ctx::Context, nf, nhe, apa, capacity = 4096)
     r = Ref{Ptr{Cvoid}}(C_NULL)
     check(ccall((:ppo_buffer_create, lib), Cint, (Ptr{Cvoid}, Int64, Cint, Cint, Cint, Ref{Ptr{Cvoid}}),
                 ctx.h, capacity, nf, nhe, apa, r))
     b = DeviceRollouts(ctx, r[], nf, nhe, apa, Float32[], Float32[], Float32[], Int64[], Float32[], UInt8[])
     finalizer(b -> (ccall((:ppo_buffer_destroy, lib), Cint, (Ptr{Cvoid},), b.h); b.h = C_NULL), b)
 end
+# BufferRollouts() takes no shapes (src/rollout_buffer.jl:9-22): this form reads them off a sample state
+DeviceRollouts(ctx::Context, state, apa::Integer; capacity = 4096) =
+    DeviceRollouts(ctx, size(state.vertex_score, 1), size(state.vertex_score, 2), apa, capacity)
 
 function flush!(b::DeviceRollouts)
     n = length(b.act)
     n == 0 && return
     GC.@preserve b begin
-        check(ccall((:ppo_buffer_append, lib), Cint,
-                    (Ptr{Cvoid}, Int64, Ptr{Float32}, Ptr{Float32}, Ptr{Int64}, Ptr{Float32}, Ptr{Float32}, Ptr{UInt8}),
-                    b.h, n, b.feat, b.mask, b.act, b.prob, b.rew, b.term))
+        if all(x -> x == round(x) && -128 <= x <= 127, b.feat)
+            # vertex scores / degrees are small integers (test/quad_game_utilities.jl:50-56): a quarter of the bytes
+            f8 = Int8.(b.feat)
+            check(ccall((:ppo_buffer_append_i8, lib), Cint,
+                        (Ptr{Cvoid}, Int64, Ptr{Int8}, Ptr{Float32}, Ptr{Int64}, Ptr{Float32}, Ptr{Float32}, Ptr{UInt8}),
+                        b.h, n, f8, b.mask, b.act, b.prob, b.rew, b.term))
+        else
+            check(ccall((:ppo_buffer_append, lib), Cint,
+                        (Ptr{Cvoid}, Int64, Ptr{Float32}, Ptr{Float32}, Ptr{Int64}, Ptr{Float32}, Ptr{Float32}, Ptr{UInt8}),
+                        b.h, n, b.feat, b.mask, b.act, b.prob, b.rew, b.term))
+        end
     end
+    # (the staged transitions stay staged when the append throws)
     empty!(b.feat); empty!(b.mask); empty!(b.prob); empty!(b.act); empty!(b.rew); empty!(b.term)
 end
 
@@ -173,6 +189,25 @@ function pull_weights!(p::DevicePolicy)
     end
 end
 
+# PPO.batch_action_probabilities(policy, state) — hook src/ProximalPolicyOptimization.jl:24, reference implementation
+# test/quad_game_utilities.jl:73-79: probs[A, nb] = softmax(reshape(policy(vertex_score), :, nb) + action_mask, dims = 1)
+function PPO.batch_action_probabilities(p::DevicePolicy, state)
+    vs = Float32.(state.vertex_score); am = Float32.(state.action_mask)
+    nhe, nb = size(vs, 2), size(vs, 3)
+    probs = Matrix{Float32}(undef, size(am, 1), nb)
+    check(ccall((:ppo_batch_action_probabilities, lib), Cint,
+                (Ptr{Cvoid}, Int64, Cint, Ptr{Float32}, Ptr{Float32}, Ptr{Float32}), p.h, nb, nhe, vs, am, probs))
+    return probs
+end
+# PPO.action_probabilities(policy, state) — hook :23, reference implementation test/quad_game_utilities.jl:65-71 (one state);
+# this is what collect_step_data! (src/collect_rollouts.jl:1-15) and single_trajectory_return (src/evaluate.jl:1-16) call
+function PPO.action_probabilities(p::DevicePolicy, state)
+    vs = reshape(Float32.(state.vertex_score), size(state.vertex_score, 1), size(state.vertex_score, 2), 1)
+    am = reshape(Float32.(state.action_mask), :, 1)
+    return vec(PPO.batch_action_probabilities(p, (vertex_score = vs, action_mask = am)))
+end
+PPO.number_of_actions_per_state(state::NamedTuple{(:vertex_score, :action_mask)}) = size(state.action_mask, 1)
+
 # Batched rollout inference (extension): collect_step_data!'s `action_probabilities` + `rand(Categorical(ap))`
 # (src/collect_rollouts.jl:1-15) for nb states at once.  vertex_score [nf, nhe, nb], action_mask [A, nb].
 function batch_sample_actions(p::DevicePolicy, vertex_score::Array{Float32,3}, action_mask::Matrix{Float32};
@@ -208,6 +243,22 @@ function DeviceAdam(p::DevicePolicy, o::Flux.Optimise.Adam)
 end
 
 # ---- the hot loop: src/train.jl ----------------------------------------------------------------------
+# step_batch!(policy, optimizer, state, linear_action_index, old_action_probabilities, advantage, epsilon,
+#             entropy_weight) — :54-84, on host arrays (state.vertex_score [nf, nhe, nb], state.action_mask [A, nb])
+function PPO.step_batch!(p::DevicePolicy, o::DeviceAdam, state, linear_action_index, old_action_probabilities, advantage,
+                         epsilon, entropy_weight)
+    vs = Float32.(state.vertex_score); am = Float32.(state.action_mask)
+    nhe, nb = size(vs, 2), size(vs, 3)
+    lin = Int64.(linear_action_index); old = Float32.(old_action_probabilities); adv = Float32.(advantage)
+    @assert length(lin) == nb && length(old) == nb && length(adv) == nb
+    pl = Ref{Cdouble}(0); el = Ref{Cdouble}(0)
+    check(ccall((:ppo_step_batch_host, lib), Cint,
+                (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Cint, Ptr{Float32}, Ptr{Float32}, Ptr{Int64}, Ptr{Float32}, Ptr{Float32},
+                 Cdouble, Cdouble, Ref{Cdouble}, Ref{Cdouble}, Ptr{Float32}),
+                p.h, o.h, nb, nhe, vs, am, lin, old, adv, epsilon, entropy_weight, pl, el, C_NULL))
+    return pl[], el[]
+end
+
 # step_epoch!(policy, optimizer, dataset, epsilon, batch_size, entropy_weight) — :86-128
 function PPO.step_epoch!(p::DevicePolicy, o::DeviceAdam, d::DeviceDataset, epsilon, batch_size, entropy_weight;
                          perm::Union{Nothing,Vector{Int64}} = nothing, seed::UInt64 = rand(UInt64))
@@ -237,6 +288,69 @@ function PPO.ppo_train!(p::DevicePolicy, o::DeviceAdam, d::DeviceDataset, epsilo
     end
     pull_weights!(p)
     return ppo_loss_history, entropy_loss_history, lr_history
+end
+
+# ---- disk replay: src/dataset.jl, src/rollouts_to_disk.jl ----------------------------------------------
+# bulk-load a DiskDataset (trajectory.csv + states/sample_i.bson, src/dataset.jl:1-52) into a device container
+function to_device(ds::PPO.DiskDataset, ctx::Context, nf, nhe, apa; n_threads = Threads.nthreads())
+    b = DeviceRollouts(ctx, nf, nhe, apa, max(length(ds), 1))
+    n = Ref{Int64}(0); has_returns = Ref{Cint}(0)
+    check(ccall((:ppo_disk_dataset_load, lib), Cint,
+                (Ptr{Cvoid}, Cstring, Cstring, Cstring, Cint, Ref{Int64}, Ref{Cint}),
+                b.h, ds.root_directory, ds.trajectory_filename, ds.states_dirname, n_threads, n, has_returns))
+    @assert n[] == length(ds)
+    return DeviceDataset(b), has_returns[] != 0
+end
+
+# ---- the outer loop: src/train.jl:164-249 ------------------------------------------------------------
+# ppo_iterate! (buffer variant, :210-249).  The rollouts are collected by the reference's own host loop
+# (collect_rollouts!, src/rollout_buffer.jl:66-79 -> collect_step_data!, which calls PPO.action_probabilities(policy,
+# state) above), stored on the device, and trained on the device; the weights are pulled back into the Flux model after
+# every ppo_train! so that evaluator(policy, env, optimizer) / BSON.@save see the update.
+function PPO.ppo_iterate!(policy::DevicePolicy, env, optimizer::DeviceAdam, episodes_per_iteration, minibatch_size,
+                          num_ppo_iterations, evaluator, epochs_per_iteration, discount, epsilon, entropy_weight)
+    loss = Dict("ppo" => [], "entropy" => [], "lr" => [])
+    apa = size(dense_layers(policy.chain)[end].weight, 1)
+    for iter in 1:num_ppo_iterations
+        evaluator(policy, env, optimizer)
+        println("\nPPO ITERATION : $iter")
+        PPO.reset!(env)
+        rollouts = DeviceRollouts(policy.ctx, PPO.state(env), apa)
+        PPO.collect_rollouts!(rollouts, env, policy, episodes_per_iteration, discount)
+        dataset = PPO.construct_dataset(rollouts)
+        ppoloss, entropyloss, lr_history = PPO.ppo_train!(policy, optimizer, dataset, epsilon, minibatch_size,
+                                                          epochs_per_iteration, entropy_weight)
+        append!(loss["ppo"], ppoloss); append!(loss["entropy"], entropyloss); append!(loss["lr"], lr_history)
+        PPO.save_loss(evaluator, loss)
+    end
+end
+
+# ppo_iterate! (disk variant, :164-202): the reference's DiskRollouts collect to state_data_path (host file I/O in its
+# own format); the finished directory is bulk-loaded into the device buffer and trained there.
+function PPO.ppo_iterate!(policy::DevicePolicy, env, optimizer::DeviceAdam, episodes_per_iteration, minibatch_size,
+                          num_ppo_iterations, evaluator, epochs_per_iteration, discount, epsilon, entropy_weight,
+                          state_data_path)
+    loss = Dict("ppo" => [], "entropy" => [], "lr" => [])
+    apa = size(dense_layers(policy.chain)[end].weight, 1)
+    for iter in 1:num_ppo_iterations
+        evaluator(policy, env, optimizer)
+        println("\nPPO ITERATION : $iter")
+        rollouts = PPO.DiskRollouts(state_data_path)
+        PPO.collect_rollouts!(rollouts, env, policy, episodes_per_iteration, discount)
+        PPO.reset!(env)
+        s = PPO.state(env)
+        dataset, has_returns = to_device(PPO.construct_dataset(rollouts), policy.ctx, size(s.vertex_score, 1),
+                                         size(s.vertex_score, 2), apa)
+        @assert has_returns
+        ppoloss, entropyloss, lr_history = PPO.ppo_train!(policy, optimizer, dataset, epsilon, minibatch_size,
+                                                          epochs_per_iteration, entropy_weight)
+        append!(loss["ppo"], ppoloss); append!(loss["entropy"], entropyloss); append!(loss["lr"], lr_history)
+        PPO.save_loss(evaluator, loss)
+    end
+    if isdir(state_data_path)
+        println("\n\nCLEARING DATA IN ROLLOUTS FOLDER :")
+        rm(state_data_path, recursive = true)
+    end
 end
 
 end # module

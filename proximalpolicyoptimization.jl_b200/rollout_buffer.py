@@ -78,7 +78,8 @@ class DeviceRollouts:
     of ``smoothed_entropy`` with s = 1f-8, below Float32 resolution.)
 
     ``update_`` stages transitions in a host chunk and appends them in batches (one H2D copy per
-    chunk instead of five ``push!`` per transition)."""
+    chunk instead of five ``push!`` per transition).  ``capacity`` is an initial reservation: like the reference's
+    ``push!``-grown vectors the device arrays grow (geometrically) when an append exceeds it."""
 
     def __init__(self, nf, nhe, apa, capacity, ctx: Context | None = None, chunk=4096):
         self.ctx = ctx or default_context()
@@ -107,6 +108,8 @@ class DeviceRollouts:
     # -- update! ------------------------------------------------------------------------------
     def update_(self, state, action_probability, action, reward, terminal):
         """``update!(episode, state, action_probability, action, reward, terminal)`` — :24-38."""
+        if self._pending == self._chunk:      # a previous flush raised: try again before staging more
+            self.flush()
         i = self._pending
         vs = np.asarray(state.vertex_score)
         am = np.asarray(state.action_mask).reshape(-1)
@@ -132,12 +135,14 @@ class DeviceRollouts:
     def flush(self):
         n = self._pending
         if n:
-            self._pending = 0
+            # (the staged transitions stay staged when the append raises, e.g. on a full buffer)
             self.append(self._s_feat[:n], self._s_mask[:n], self._s_prob[:n], self._s_act[:n], self._s_rew[:n],
                         self._s_term[:n])
+            self._pending = 0
 
     def append(self, feat, mask, action_probability, action, reward, terminal):
-        """Batched ``update!``: n transitions at once.  feat [n, nhe, nf] float32 or int64."""
+        """Batched ``update!``: n transitions at once.  feat [n, nhe, nf] float32, int64 (the reference's
+        ``Matrix{Int64}`` scores) or int8 / int16 (narrowed by the caller: exact, 4x / 2x fewer host->device bytes)."""
         feat = np.asarray(feat)
         n = feat.shape[0] if feat.ndim == 3 else feat.size // (self.nhe * self.nf)
         mask = np.ascontiguousarray(mask, np.float32).reshape(n, self.A)
@@ -146,11 +151,13 @@ class DeviceRollouts:
         rew = np.ascontiguousarray(reward, np.float32).reshape(n)
         term = np.ascontiguousarray(np.asarray(terminal).astype(np.uint8)).reshape(n)
         lib = _lib.load()
-        if feat.dtype == np.int64:
+        ints = {np.dtype(np.int64): (lib.ppo_buffer_append_i64, C.c_int64), np.dtype(np.int8): (lib.ppo_buffer_append_i8, C.c_int8),
+                np.dtype(np.int16): (lib.ppo_buffer_append_i16, C.c_int16)}
+        if feat.dtype in ints:
+            fn, ct = ints[feat.dtype]
             f = np.ascontiguousarray(feat).reshape(n, self.nhe, self.nf)
-            _lib.check(lib.ppo_buffer_append_i64(self.handle, n, _lib.ptr(f, C.c_int64), _lib.ptr(mask, C.c_float),
-                                                 _lib.ptr(act, C.c_int64), _lib.ptr(prob, C.c_float),
-                                                 _lib.ptr(rew, C.c_float), _lib.ptr(term, C.c_uint8)))
+            _lib.check(fn(self.handle, n, _lib.ptr(f, ct), _lib.ptr(mask, C.c_float), _lib.ptr(act, C.c_int64),
+                          _lib.ptr(prob, C.c_float), _lib.ptr(rew, C.c_float), _lib.ptr(term, C.c_uint8)))
         else:
             f = np.ascontiguousarray(feat, np.float32).reshape(n, self.nhe, self.nf)
             _lib.check(lib.ppo_buffer_append(self.handle, n, _lib.ptr(f, C.c_float), _lib.ptr(mask, C.c_float),

@@ -19,16 +19,24 @@ RETURNS_HEADER = ["sample_names", "selected_actions", "selected_action_probabili
 
 
 def _julia_float(x):
-    """Julia's shortest round-trip printing of a Float32/Float64: 6.0, 0.2, 1.0e-5, 1.0e10."""
+    """Julia's shortest round-trip printing of a Float32/Float64 (what CSV.jl writes): 6.0, 0.2, 1.0e-5, 123456.7,
+    1.0e6, 1.234567e6 -- plain notation for 1e-5 < |x| < 1e6, exponent notation outside."""
     r = str(x) if isinstance(x, np.float32) else repr(float(x))
+    if r in ("inf", "-inf", "nan"):
+        return {"inf": "Inf", "-inf": "-Inf", "nan": "NaN"}[r]
     if "e" in r:
         m, e = r.split("e")
         if "." not in m:
             m += ".0"
-        r = f"{m}e{int(e)}"
-    elif "." not in r and r not in ("inf", "-inf", "nan"):
+        return f"{m}e{int(e)}"
+    if "." not in r:
         r += ".0"
-    return {"inf": "Inf", "-inf": "-Inf", "nan": "NaN"}.get(r, r)
+    if abs(float(x)) >= 1e6:                     # Python keeps plain notation up to 1e16, Julia only below 1e6
+        sign = "-" if r.startswith("-") else ""
+        ip, fp = r.lstrip("-").split(".")
+        digits = (ip + fp).rstrip("0") or "0"
+        return f"{sign}{digits[0]}.{digits[1:] or '0'}e{len(ip) - 1}"
+    return r
 
 
 def _fmt(x):

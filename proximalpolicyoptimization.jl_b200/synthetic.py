@@ -107,13 +107,15 @@ def make_actions(rng, mask):
     return (np.argmax(score, axis=1) + 1).astype(np.int64)
 
 
-def make_buffer(cfg: Config, n=None, chunk=65536, alloc=None):
+def make_buffer(cfg: Config, n=None, chunk=65536, alloc=None, feat_dtype=np.float32):
     """All rollout arrays except the old action probabilities (they need the policy).  ``alloc(shape, dtype)``
-    optionally provides the output arrays (e.g. pinned host memory) so that large configs are generated in place."""
+    optionally provides the output arrays (e.g. pinned host memory) so that large configs are generated in place.
+    ``feat_dtype``: the features are small integers (vertex scores / degrees); np.int8 keeps them as the narrow integers
+    ``ppo_buffer_append_i8`` takes (same values, same random stream)."""
     n = cfg.N if n is None else n
     rng = rng_for(cfg, 0)
     alloc = alloc or (lambda shape, dtype: np.empty(shape, dtype))
-    feat = alloc((n, cfg.nhe, cfg.nf), np.float32)
+    feat = alloc((n, cfg.nhe, cfg.nf), feat_dtype)
     for s in range(0, n, chunk):
         e = min(n, s + chunk)
         feat[s:e] = rng.integers(-3, 9, size=(e - s, cfg.nhe, cfg.nf), dtype=np.int8)

@@ -152,6 +152,28 @@ def test_buffer_roundtrip_and_gather_bit_exact(ctx, key):
     buf.close()
 
 
+@pytest.mark.parametrize("dtype", [np.int8, np.int16, np.int64])
+def test_integer_feature_append_is_exact(ctx, dtype):
+    """StateData.vertex_score is a Matrix{Int64} of small integers (test/quad_game_utilities.jl:50-56): the Int64 entry
+    point and the narrowed Int8 / Int16 ones (4x / 2x fewer host->device bytes) must land the same Float32 features as the
+    Float32 append, also across a growth of the buffer and for row counts that are not multiples of 16."""
+    nf, nhe, apa = 9, 3, 2
+    rng = np.random.default_rng(3)
+    lim = {np.int8: 127, np.int16: 32767, np.int64: 10 ** 6}[dtype]
+    buf = P.DeviceRollouts(nf, nhe, apa, 5, ctx)
+    ref = P.DeviceRollouts(nf, nhe, apa, 64, ctx)
+    for n in (1, 7, 33):
+        f = rng.integers(-lim - 1, lim + 1, (n, nhe, nf)).astype(dtype)
+        m = np.zeros((n, nhe * apa), np.float32)
+        args = (m, np.full(n, 0.5, np.float32), np.ones(n, np.int64), np.arange(n, dtype=np.float32), np.zeros(n, bool))
+        buf.append(f, *args)
+        ref.append(f.astype(np.float32), *args)
+    a, b = buf.read(), ref.read()
+    for k in a:
+        assert np.array_equal(a[k], b[k]), k
+    buf.close(); ref.close()
+
+
 def test_gather_variants_agree_bit_exact(ctx):
     # LDG/STG path (variant 0) and TMA bulk-copy ring (variant 1, cp.async.bulk) against the oracle
     import ctypes as C
@@ -400,8 +422,9 @@ def test_error_behaviour(ctx):
     with pytest.raises(P.PPOError):      # action outside 1..A
         buf.append(f, m, np.ones(3), np.array([1, 5, 2]), np.zeros(3), np.zeros(3))
     buf.append(f, m, np.ones(3), np.array([1, 4, 2]), np.zeros(3), np.zeros(3))
-    with pytest.raises(P.PPOError):      # capacity
-        buf.append(np.zeros((6, 2, 4), np.float32), np.zeros((6, 4), np.float32), np.ones(6), np.ones(6), np.zeros(6), np.zeros(6))
+    # the capacity is an initial reservation: like the reference's push!-grown vectors the buffer grows on demand
+    buf.append(np.ones((6, 2, 4), np.float32), np.zeros((6, 4), np.float32), np.ones(6), np.ones(6), np.zeros(6), np.zeros(6))
+    assert len(buf) == 9 and np.array_equal(buf.read()["feat"][:3], f) and np.all(buf.read()["feat"][3:] == 1.0)
     ds = P.construct_dataset(buf)
     with pytest.raises(P.PPOError):      # index outside 1..length
         ds[np.array([0, 1])]
