@@ -327,10 +327,13 @@ class Harness:
         return ms / steps, clocks, launches
 
 
-def run_update_legs(h, cfg, B_local, gemm_mode, data, W, b, steps, warmup, feat_key="feat", sample_clocks=True, e2e=True):
-    """resident + end-to-end legs of one workload; returns a dict of raw measurements"""
+def run_update_legs(h, cfg, B_local, gemm_mode, data, W, b, steps, warmup, feat_key="feat", sample_clocks=True, e2e=True,
+                    compact=True):
+    """resident + end-to-end legs of one workload; returns a dict of raw measurements.  compact: token compaction (the
+    library's default: the MLP skips tokens all of whose actions are masked; exact zeros either way)"""
     P = h.P
     pol = P.Policy(cfg.nf, cfg.H, cfg.L, cfg.apa, h.ctx, weights=W, biases=b, gemm_mode=gemm_mode)
+    pol.set_token_compaction(compact)
     if h.use_p2p:
         h.D.enable_p2p_gradients(pol)
     opt = P.Optimiser(P.Adam(ETA))
@@ -354,7 +357,7 @@ def run_update_legs(h, cfg, B_local, gemm_mode, data, W, b, steps, warmup, feat_
 
     ms_step, clocks, launches = h.timed(resident_step, steps, warmup, f"{cfg.name} resident", sample_clocks)
     out = {"ms_step": ms_step, "clocks": clocks, "launches": launches, "engine": pol.gemm_mode,
-           "nbatches": (cfg.N + B_local - 1) // B_local}
+           "nbatches": (cfg.N + B_local - 1) // B_local, "active_tokens_last_minibatch": pol.active_tokens()}
     if e2e:
         def e2e_step(i):
             fill()
@@ -652,6 +655,18 @@ def _run_ours(args):
     e2e = {"value": cfg.N * world / (main["ms_e2e"] * 1e-3), "unit": UNIT,
            "h2d_bytes_per_step": cfg.N * host_bytes_per_transition(cfg, feat_dtype),
            "d2h_bytes_per_step": 16 * main["nbatches"], "ms_per_step": main["ms_e2e"], "steps": args.steps}
+    # token compaction is the library default; the same steps with every token pushed through the MLP (what the
+    # reference does with fully masked tokens) are timed beside it
+    last_rows = (cfg.N - (main["nbatches"] - 1) * B_local) * cfg.nhe
+    config["token_compaction"] = {
+        "enabled": main["active_tokens_last_minibatch"] >= 0,
+        "active_token_fraction_last_minibatch": round(main["active_tokens_last_minibatch"] / last_rows, 4),
+        "mask": "synthetic.make_masks: groups of 4 tokens, inactive with p = 0.25, first group active (SURVEY 8(d))"}
+    if args.gemm == "f16x3" and not args.no_extras:
+        dense = run_update_legs(h, cfg, B_local, gemm_mode, data, W, b, min(args.steps, 3), 3, sample_clocks=False,
+                                e2e=False, compact=False)
+        config["token_compaction"]["value_with_every_token"] = cfg.N * world / (dense["ms_step"] * 1e-3)
+        config["token_compaction"]["ms_per_step_with_every_token"] = dense["ms_step"]
     del data
 
     extras, errors = {}, {}

@@ -168,12 +168,23 @@ int ppo_policy_write(ppo_policy* p, const float* const* W, const float* const* b
 int ppo_policy_set_gemm_mode(ppo_policy* p, int mode);
 /* the engine in use (after PPO_GEMM_AUTO: the one that was picked) */
 int ppo_policy_get_gemm_mode(ppo_policy* p);
+/* Token compaction (fp16-split engine; on by default).  A token all of whose actions carry a -Inf mask has probability
+ * exactly 0 for each of them (softmax(logits .+ mask), test/quad_game_utilities.jl:73-79), so its logits never reach the
+ * loss and its rows add exact zeros to every gradient.  With compaction the MLP runs on the remaining tokens only
+ * (inactive quads of a padded mesh, test/quad_game_utilities.jl:39-44; states padded by pad_action_mask,
+ * examples/triangle/distance_weighted/triangle_utilities.jl:41-55); losses, probabilities and gradients are those of
+ * the dense evaluation up to the summation order of the weight gradient.  enable = 0 runs every token. */
+int ppo_policy_set_token_compaction(ppo_policy* p, int enable);
+/* tokens the last forward pass ran (-1: it ran every token of the minibatch); synchronises */
+int ppo_policy_active_tokens(ppo_policy* p, int64_t* active_out);
+#define PPO_GATE_SKIPPED 255
 /* Parity instrumentation: the leakyrelu' branch (1 = pre-activation > 0, 0 = slope branch) that the backward pass of
  * the LAST minibatch applies to every element of hidden activation `layer` (1 .. n_layers-1, the output of Dense
  * `layer`), gates_out[rows][dims[layer]], rows = tokens of that minibatch.  leakyrelu' is discontinuous at 0
  * (ASSUMED NNlib.leakyrelu, test/policy.jl:11-15), so a gradient comparison against another evaluation is only
  * meaningful when both sides take the same branch for pre-activations within rounding of zero; the tests feed these
- * gates to the fp64 oracle and check separately that every disagreement sits at a ~0 pre-activation. */
+ * gates to the fp64 oracle and check separately that every disagreement sits at a ~0 pre-activation.  Tokens that a
+ * compacted pass skipped read PPO_GATE_SKIPPED (their gate multiplies an exact zero). */
 int ppo_policy_read_gates(ppo_policy* p, int layer, int64_t rows, uint8_t* gates_out);
 /* Data parallelism over NVLink peer memory (one process per GPU, one node): instead of an NCCL all-reduce per minibatch the
    Adam kernel reads every rank's published gradient through CUDA-IPC mappings and adds them in rank order (weights stay

@@ -416,6 +416,8 @@ def policy_gradient(policy: Policy, feat, mask, actions1, old_probs, advantage, 
     discontinuous at 0, so two evaluations that round differently can take different branches for a pre-activation
     within rounding of zero; handing the device's branches (ppo_policy_read_gates) to the oracle makes the gradient
     comparison well posed, and the tests check separately that every disagreement sits at such a pre-activation.
+    A gate value of 255 (PPO_GATE_SKIPPED: a token the device's compacted MLP never ran because all of its actions are
+    masked) keeps this evaluation's own branch; the tests assert that the incoming gradient of such a row is exactly 0.
     ``nb_total``: see :func:`loss_grad_logits`."""
     nb = feat.shape[0]
     dt = policy.W[0].dtype
@@ -433,7 +435,10 @@ def policy_gradient(policy: Policy, feat, mask, actions1, old_probs, advantage, 
         db[l] = delta.sum(axis=0)
         if l > 0:
             dx = delta @ policy.W[l].T
-            pos = (acts[l] > 0) if gates is None else np.asarray(gates[l]).astype(bool)
+            pos = acts[l] > 0
+            if gates is not None:
+                gl = np.asarray(gates[l])
+                pos = np.where(gl == 255, pos, gl.astype(bool)) if gl.dtype == np.uint8 else gl.astype(bool)
             delta = np.where(pos, dx, dt.type(getattr(policy, "slope", LEAKY_SLOPE)) * dx)
     out = (ppoloss, F64(entropyloss) * F64(entropy_weight), dW, db)
     return out + (acts,) if return_acts else out

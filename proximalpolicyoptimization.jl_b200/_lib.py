@@ -63,6 +63,8 @@ SIGNATURES = {
     "ppo_policy_set_gemm_mode": (c_int, [vp, c_int]),
     "ppo_policy_get_gemm_mode": (c_int, [vp]),
     "ppo_policy_read_gates": (c_int, [vp, c_int, c_i64, PU8]),
+    "ppo_policy_set_token_compaction": (c_int, [vp, c_int]),
+    "ppo_policy_active_tokens": (c_int, [vp, PI64]),
     "ppo_policy_p2p_export": (c_int, [vp, vp]),
     "ppo_policy_p2p_connect": (c_int, [vp, c_int, c_int, vp]),
     "ppo_policy_num_params": (c_i64, [vp]),

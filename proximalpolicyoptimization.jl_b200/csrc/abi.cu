@@ -118,6 +118,9 @@ int ensure_workspace(ppo_policy* p, int64_t tokens) {
     for (int l = 1; l < L; ++l) hmax = std::max(hmax, p->dims[l]);
     p->act.assign(L + 1, nullptr);
     for (int l = 1; l <= L; ++l) PPO_TRY(dev_alloc(&p->act[l], (size_t)tokens * p->dims[l]));
+    // the logits start out as zeros: a compacted forward pass leaves the logits of skipped (fully masked) tokens untouched,
+    // and the loss adds their -Inf mask to whatever finite value is there
+    PPO_CUDA(cudaMemsetAsync(p->act[L], 0, (size_t)tokens * p->dims[L] * sizeof(float), ctx->stream));
     PPO_TRY(dev_alloc(&p->dact[0], (size_t)tokens * hmax));
     PPO_TRY(dev_alloc(&p->dact[1], (size_t)tokens * hmax));
     PPO_TRY(dev_alloc(&p->dlogits, (size_t)tokens * p->dims[L]));
@@ -153,11 +156,12 @@ int refresh_engine_weights(ppo_policy* p) {
     return PPO_OK;
 }
 
-// forward through all Dense layers: act[l] for l = 1..L  (act[L] = logits, linear)
-int policy_forward(ppo_policy* p, const float* X, int64_t M) {
+// forward through all Dense layers: act[l] for l = 1..L  (act[L] = logits, linear).  mask: the action mask the logits
+// will be added to (lets the fp16-split engine skip fully masked tokens), or nullptr
+int policy_forward(ppo_policy* p, const float* X, int64_t M, const float* mask) {
     ppo_ctx* ctx = p->ctx;
     const int L = p->L;
-    if (p->gemm_mode == PPO_GEMM_F16X3_TC) return f16_forward(p, X, M);
+    if (p->gemm_mode == PPO_GEMM_F16X3_TC) return f16_forward(p, X, M, mask);
     const float* in = X;
     for (int l = 0; l < L; ++l) {
         const int K = p->dims[l], N = p->dims[l + 1];
@@ -223,7 +227,7 @@ int step_core(ppo_policy* p, ppo_opt* opt, const ppo_batch& bt, int64_t nb, int 
     const int64_t M = nb * nhe;
     PPO_TRY(ensure_workspace(p, M));
     PPO_TRY(ensure_loss_buffers(p, nb, A, slot + 1));
-    PPO_TRY(policy_forward(p, bt.feat, M));
+    PPO_TRY(policy_forward(p, bt.feat, M, bt.mask));
     PPO_TRY(launch_loss(ctx, p->act[L], bt.mask, bt.action, bt.old_prob, bt.adv, nb, A, epsilon, entropy_weight,
                         inv_nb_global, p->dlogits, p->d_loss_partials, p->d_loss_hist + (d_step ? 0 : 2 * slot), nullptr,
                         d_step));
@@ -903,6 +907,20 @@ int ppo_policy_p2p_connect(ppo_policy* p, int nranks, int rank, const void* hand
 
 int ppo_policy_get_gemm_mode(ppo_policy* p) { return p ? p->gemm_mode : PPO_ERR_INVALID; }
 
+int ppo_policy_set_token_compaction(ppo_policy* p, int enable) {
+    PPO_REQUIRE(p != nullptr, "set_token_compaction: null policy");
+    p->compact_tokens = enable ? 1 : 0;
+    return PPO_OK;
+}
+
+int ppo_policy_active_tokens(ppo_policy* p, int64_t* active_out) {
+    PPO_REQUIRE(p != nullptr && active_out != nullptr, "active_tokens: null argument");
+    PPO_TRY(use(p->ctx));
+    *active_out = -1;
+    if (p->gemm_mode == PPO_GEMM_F16X3_TC && p->f16 != nullptr) return f16_active_tokens(p, active_out);
+    return PPO_OK;
+}
+
 int ppo_policy_read_gates(ppo_policy* p, int layer, int64_t rows, uint8_t* gates_out) {
     PPO_REQUIRE(p != nullptr && gates_out != nullptr, "read_gates: null argument");
     ppo_ctx* ctx = p->ctx;
@@ -951,7 +969,7 @@ static int probabilities_to_scratch(ppo_policy* p, int64_t nb, int nhe, const fl
     PPO_TRY(ensure_workspace(p, M));
     PPO_TRY(ensure_loss_buffers(p, nb, A, 1));
     PPO_TRY(ensure_scratch(ctx, (size_t)nb * A * 4 + extra_scratch));
-    PPO_TRY(policy_forward(p, p->hbatch.feat, M));
+    PPO_TRY(policy_forward(p, p->hbatch.feat, M, p->hbatch.mask));
     return launch_loss(ctx, p->act[p->L], p->hbatch.mask, p->hbatch.action, p->hbatch.old_prob, p->hbatch.adv, nb, A,
                        0.0, 0.0, 1.0 / (double)nb, nullptr, p->d_loss_partials, p->d_loss_hist, (float*)ctx->d_scratch);
 }

@@ -119,6 +119,7 @@ struct ppo_policy {
     int64_t P = 0;
     float slope = 0.01f;
     int gemm_mode = PPO_GEMM_FP32_SIMT;
+    int compact_tokens = 1;          // fp16-split engine: run the MLP only on tokens with an unmasked action (ppo_policy_set_token_compaction)
     float* params = nullptr;  // flat, Flux.params order: W1[in][out], b1, W2, b2, ...
     float* grads = nullptr;   // same layout
     // workspace for M = rows*nhe tokens

@@ -264,6 +264,14 @@ narrow_to_f32_kernel(const T* __restrict__ s, float* __restrict__ d, int64_t n) 
     if (blockIdx.x == 0 && tail < n) d[tail] = (float)s[tail];      // < 16 leftover elements
 }
 
+// element-wise variant for a destination that is not 16-byte aligned (an append at an odd element offset)
+template <typename T>
+__global__ void __launch_bounds__(256)
+narrow_to_f32_scalar_kernel(const T* __restrict__ s, float* __restrict__ d, int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        d[i] = (float)s[i];
+}
+
 inline unsigned grid_for(ppo_ctx* ctx, int64_t n, int per_block, int waves = 8) {
     int64_t want = ceil_div(n, per_block);
     int64_t cap = (int64_t)ctx->num_sms * waves;
@@ -368,10 +376,15 @@ int launch_i64_to_f32(ppo_ctx* ctx, const int64_t* src, float* dst, int64_t n) {
 
 int launch_narrow_to_f32(ppo_ctx* ctx, const void* src, int elem_bytes, float* dst, int64_t n) {
     if (n <= 0) return PPO_OK;
-    PPO_REQUIRE(((uintptr_t)src % 16 == 0) && ((uintptr_t)dst % 16 == 0), "narrow_to_f32: unaligned buffers");
-    const unsigned grid = grid_for(ctx, n / 16 + 1, 256, 16);
-    if (elem_bytes == 1) narrow_to_f32_kernel<int8_t><<<grid, 256, 0, ctx->stream>>>((const int8_t*)src, dst, n);
-    else narrow_to_f32_kernel<int16_t><<<grid, 256, 0, ctx->stream>>>((const int16_t*)src, dst, n);
+    if (((uintptr_t)src % 16 == 0) && ((uintptr_t)dst % 16 == 0)) {
+        const unsigned grid = grid_for(ctx, n / 16 + 1, 256, 16);
+        if (elem_bytes == 1) narrow_to_f32_kernel<int8_t><<<grid, 256, 0, ctx->stream>>>((const int8_t*)src, dst, n);
+        else narrow_to_f32_kernel<int16_t><<<grid, 256, 0, ctx->stream>>>((const int16_t*)src, dst, n);
+    } else {
+        const unsigned grid = grid_for(ctx, n, 256, 16);
+        if (elem_bytes == 1) narrow_to_f32_scalar_kernel<int8_t><<<grid, 256, 0, ctx->stream>>>((const int8_t*)src, dst, n);
+        else narrow_to_f32_scalar_kernel<int16_t><<<grid, 256, 0, ctx->stream>>>((const int16_t*)src, dst, n);
+    }
     ctx->launches += 1;
     PPO_CUDA(cudaGetLastError());
     return PPO_OK;

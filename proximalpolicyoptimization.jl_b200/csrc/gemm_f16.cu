@@ -111,7 +111,11 @@ __host__ __device__ inline size_t sign_index(int64_t row, int w, int nwords) {
 inline size_t sign_words(int64_t rows, int N) { return (size_t)ceil_div(rows, 128) * 128 * (N / 32); }
 
 struct KK16Params {
-    int M, N, K;
+    int M, N, K;             // M: rows the host sized grids / tensor maps for (>= the rows actually in use)
+    // rows actually in use, read on the device (token compaction: the number of active tokens of a minibatch is only known
+    // there); nullptr = M.  Tiles past that count are not computed; the rows between it and the end of its tile are
+    // (dgrad writes zeros there and keeps them out of the column sums).
+    const int* M_dev;
     int tiles_m, tiles_n, k_blocks;
     int epi;
     int act;                 // fwd: apply leakyrelu
@@ -227,7 +231,12 @@ f16_gemm_kk_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
     const int rank = TWO ? (int)cluster_ctarank() : 0;
     const int unit0 = TWO ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
     const int unit_step = TWO ? (int)(gridDim.x >> 1) : (int)gridDim.x;
-    const int num_tiles = (TWO ? (p.tiles_m + 1) / 2 : p.tiles_m) * p.tiles_n;
+    // rows in use (token compaction: known only on the device).  Rows between that count and the end of the last tile are
+    // computed like any other: the producers keep them finite (zeros / bounded stale values, see split16_rows_kernel), and
+    // every consumer either stops at the row count or multiplies them by exact zeros.
+    const int M_rows = p.M_dev != nullptr ? min(__ldg(p.M_dev), p.M) : p.M;
+    const int tiles_m = (M_rows + F_BM - 1) / F_BM;
+    const int num_tiles = (TWO ? (tiles_m + 1) / 2 : tiles_m) * p.tiles_n;
     const int chunks_per_tile = (p.k_blocks + p.chunk_kb - 1) / p.chunk_kb;
     auto m_tile_of = [&](int unit) -> int { return TWO ? 2 * (unit / p.tiles_n) + rank : unit / p.tiles_n; };
 
@@ -335,9 +344,9 @@ f16_gemm_kk_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
         uint32_t cc = 0;
         for (int tile = unit0; tile < num_tiles; tile += unit_step) {
             const int mt = m_tile_of(tile);
-            const bool mt_valid = mt < p.tiles_m;
             const int m0 = mt * F_BM, n0 = (tile % p.tiles_n) * BN;
             const int row = m0 + row_in_tile;
+            const bool mt_valid = mt < tiles_m;
             float s[CPT];
 #pragma unroll
             for (int j = 0; j < CPT; ++j) s[j] = 0.0f;
@@ -347,7 +356,7 @@ f16_gemm_kk_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
 #pragma unroll
                 for (int g = 0; g < CPT / 32; ++g) {
                     const int col0 = n0 + cq * CPT + g * 32;
-                    gbits[g] = (row < p.M && col0 < p.N) ? __ldg(p.gate + sign_index(row, col0 >> 5, p.N >> 5)) : 0u;
+                    gbits[g] = (row < M_rows && col0 < p.N) ? __ldg(p.gate + sign_index(row, col0 >> 5, p.N >> 5)) : 0u;
                 }
             }
             for (int ch = 0; ch < chunks_per_tile; ++ch, ++cc) {
@@ -396,7 +405,7 @@ f16_gemm_kk_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
                     }
                     if (p.signs_out != nullptr && col0 < p.N && mt_valid) p.signs_out[sign_index(row, col0 >> 5, p.N >> 5)] = w;
                 } else {
-                    const float inb = (row < p.M) ? unscale : 0.0f;     // rows beyond M: keep them out of the column sums
+                    const float inb = (row < M_rows) ? unscale : 0.0f;     // rows beyond the data: keep them out of the column sums
                     const float ins = inb * p.slope;
                     const uint32_t w = gbits[g];
 #pragma unroll
@@ -453,8 +462,9 @@ f16_gemm_kk_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
 struct MN16Params {
     int Kin, Nout;
     int64_t M;
+    const int* M_dev;         // rows actually in use (device-side, see KK16Params::M_dev); nullptr = M
     int tiles_k, tiles_n, splits;
-    int64_t rows_per_split;   // multiple of F_CHUNK_KB * F_BK
+    int64_t rows_per_split;   // multiple of F_CHUNK_KB * F_BK (recomputed on the device when M_dev is set)
     float* partial;           // [splits][Kin][Nout]
 };
 
@@ -479,9 +489,15 @@ f16_gemm_mn_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
     const int tile = blockIdx.x % (p.tiles_k * p.tiles_n);
     const int split = blockIdx.x / (p.tiles_k * p.tiles_n);
     const int kin0 = (tile / p.tiles_n) * F_BM, n0 = (tile % p.tiles_n) * BN;
-    const int64_t r_begin = (int64_t)split * p.rows_per_split;
-    int64_t r_end = r_begin + p.rows_per_split;
-    if (r_end > p.M) r_end = p.M;
+    int64_t M_rows = p.M, rows_per_split = p.rows_per_split;
+    if (p.M_dev != nullptr) {
+        M_rows = min((int64_t)__ldg(p.M_dev), p.M);
+        constexpr int64_t G = F_CHUNK_KB * F_BK;
+        rows_per_split = ((M_rows + p.splits - 1) / p.splits + G - 1) / G * G;
+    }
+    const int64_t r_begin = (int64_t)split * rows_per_split;
+    int64_t r_end = r_begin + rows_per_split;
+    if (r_end > M_rows) r_end = M_rows;
     const int k_blocks = r_end > r_begin ? (int)((r_end - r_begin + F_BK - 1) / F_BK) : 0;
     const int chunks = (k_blocks + F_CHUNK_KB - 1) / F_CHUNK_KB;
 
@@ -847,9 +863,15 @@ head_finish_kernel(const float* __restrict__ scratch, int chunks, int K, int N, 
 
 // stage 1 of folding the dgrad epilogue's per-quarter column sums: block (x = column block, y = row chunk)
 __global__ void __launch_bounds__(256)
-f16_colsum_fold_kernel(const float* __restrict__ part, int64_t rows, int N, int64_t rows_per_chunk, float* __restrict__ out) {
+f16_colsum_fold_kernel(const float* __restrict__ part, int64_t rows, int N, int64_t rows_per_chunk, float* __restrict__ out,
+                       const int* __restrict__ M_dev = nullptr) {
     const int n = blockIdx.x * 256 + threadIdx.x;
     if (n >= N) return;
+    if (M_dev != nullptr) {      // per-quarter column sums of a dgrad over *M_dev rows: 4 partial rows per 128-row tile
+        const int64_t r = 4 * (((int64_t)__ldg(M_dev) + F_BM - 1) / F_BM);
+        rows = r < rows ? r : rows;
+        rows_per_chunk = (rows + gridDim.y - 1) / gridDim.y;
+    }
     const int64_t r0 = (int64_t)blockIdx.y * rows_per_chunk;
     const int64_t r1 = r0 + rows_per_chunk < rows ? r0 + rows_per_chunk : rows;
     float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
@@ -862,6 +884,137 @@ f16_colsum_fold_kernel(const float* __restrict__ part, int64_t rows, int N, int6
 }
 
 // ---------------------------------------------------------------------------------------------
+// token compaction.  A token (half-edge) all of whose apa actions carry a -Inf mask has probability exactly 0 for each of
+// them (softmax(logits + mask), test/quad_game_utilities.jl:73-79): its logits never reach the loss and its dlogits are
+// exactly 0, so its rows contribute exact zeros to every weight / bias gradient.  The reference still pushes those rows
+// through the MLP (inactive quads of a padded mesh: test/quad_game_utilities.jl:39-44; padded states:
+// examples/triangle/distance_weighted/triangle_utilities.jl:31-55).  Here the MLP runs on the ACTIVE tokens only: a
+// deterministic two-pass stream compaction builds row -> token (ascending), the input split gathers those rows, every
+// GEMM reads the row count from device memory, and the head scatters the logits back to their dense positions.
+// ---------------------------------------------------------------------------------------------
+constexpr int TOK_THREADS = 1024;
+constexpr int TOK_PER_THREAD = 4;
+constexpr int TOK_PER_BLOCK = TOK_THREADS * TOK_PER_THREAD;
+
+__device__ __forceinline__ bool token_active(const float* __restrict__ mask, int64_t t, int apa) {
+    bool a = false;
+    if (apa == 4) {
+        const float4 m = __ldg(reinterpret_cast<const float4*>(mask) + t);
+        a = (m.x != -INFINITY) | (m.y != -INFINITY) | (m.z != -INFINITY) | (m.w != -INFINITY);
+    } else {
+        for (int j = 0; j < apa; ++j) a |= (__ldg(mask + t * apa + j) != -INFINITY);
+    }
+    return a;
+}
+// block-wide sum of one int per thread (1024 threads); every thread gets the total
+__device__ __forceinline__ int block_sum_1024(int v, int* sm /*[32]*/) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = v;
+    __syncthreads();
+    int r = sm[threadIdx.x & 31];
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) r += __shfl_xor_sync(0xffffffffu, r, d);
+    return r;
+}
+__global__ void __launch_bounds__(TOK_THREADS)
+token_count_kernel(const float* __restrict__ mask, int64_t M, int apa, int* __restrict__ blk_counts) {
+    __shared__ int sm[32];
+    const int64_t t0 = (int64_t)blockIdx.x * TOK_PER_BLOCK + (int64_t)threadIdx.x * TOK_PER_THREAD;
+    int c = 0;
+#pragma unroll
+    for (int j = 0; j < TOK_PER_THREAD; ++j)
+        if (t0 + j < M) c += token_active(mask, t0 + j, apa) ? 1 : 0;
+    c = block_sum_1024(c, sm);
+    if (threadIdx.x == 0) blk_counts[blockIdx.x] = c;
+}
+__global__ void __launch_bounds__(TOK_THREADS)
+token_compact_kernel(const float* __restrict__ mask, int64_t M, int apa, const int* __restrict__ blk_counts,
+                     int* __restrict__ tok_of_row, int* __restrict__ rows_out) {
+    __shared__ int sm[32];
+    __shared__ int wsum[32];
+    int before = 0;
+    for (int i = threadIdx.x; i < (int)blockIdx.x; i += TOK_THREADS) before += blk_counts[i];
+    before = block_sum_1024(before, sm);
+    const int64_t t0 = (int64_t)blockIdx.x * TOK_PER_BLOCK + (int64_t)threadIdx.x * TOK_PER_THREAD;
+    bool a[TOK_PER_THREAD];
+    int c = 0;
+#pragma unroll
+    for (int j = 0; j < TOK_PER_THREAD; ++j) {
+        a[j] = (t0 + j < M) && token_active(mask, t0 + j, apa);
+        c += a[j] ? 1 : 0;
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int incl = c;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int o = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += o;
+    }
+    if (lane == 31) wsum[warp] = incl;
+    __syncthreads();
+    int wprefix = 0, total = 0;
+    {
+        const int wv = wsum[lane];
+        int wincl = wv;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int o = __shfl_up_sync(0xffffffffu, wincl, d);
+            if (lane >= d) wincl += o;
+        }
+        wprefix = __shfl_sync(0xffffffffu, wincl - wv, warp);
+        total = __shfl_sync(0xffffffffu, wincl, 31);
+    }
+    int r = before + wprefix + incl - c;
+#pragma unroll
+    for (int j = 0; j < TOK_PER_THREAD; ++j)
+        if (a[j]) tok_of_row[r++] = (int)(t0 + j);
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) *rows_out = before + total;
+}
+// gathering split: row r of (hi, lo) = features of token tok_of_row[r] * scale; 8 elements per thread
+// Rows between the data and the end of the last 256-row unit (what a CTA pair's tile can touch) are zeroed: the forward
+// GEMMs compute them like any other row (their activations are leakyrelu(bias): finite and inside the planned bounds).
+__global__ void __launch_bounds__(256)
+split16_rows_kernel(const float* __restrict__ x, const int* __restrict__ tok_of_row, const int* __restrict__ rows_dev, int K8,
+                    __half* __restrict__ hi, __half* __restrict__ lo, const float* sc, int64_t rows_alloc) {
+    const float s = __ldg(sc);
+    const int64_t rows = __ldg(rows_dev);
+    const int64_t n8 = rows * K8;
+    {
+        const int64_t end = min((rows + 255) / 256 * 256, rows_alloc);
+        for (int64_t i = n8 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < end * K8; i += (int64_t)gridDim.x * blockDim.x) {
+            reinterpret_cast<uint4*>(hi)[i] = make_uint4(0u, 0u, 0u, 0u);
+            reinterpret_cast<uint4*>(lo)[i] = make_uint4(0u, 0u, 0u, 0u);
+        }
+    }
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / K8;
+        const int c = (int)(i - r * K8);
+        const float4* src = reinterpret_cast<const float4*>(x + ((int64_t)__ldg(tok_of_row + r) * K8 + c) * 8);
+        const float4 a = __ldcs(src), b = __ldcs(src + 1);
+        uint4 h, l;
+        f16_split2(a.x * s, a.y * s, h.x, l.x);
+        f16_split2(a.z * s, a.w * s, h.y, l.y);
+        f16_split2(b.x * s, b.y * s, h.z, l.z);
+        f16_split2(b.z * s, b.w * s, h.w, l.w);
+        reinterpret_cast<uint4*>(hi)[i] = h;
+        reinterpret_cast<uint4*>(lo)[i] = l;
+    }
+}
+// gates of compacted rows -> dense token order; tokens the MLP skipped get PPO_GATE_SKIPPED (their gate multiplies an
+// exact zero)
+__global__ void __launch_bounds__(256)
+gates_scatter_kernel(const uint8_t* __restrict__ rows_gates, const int* __restrict__ tok_of_row, const int* __restrict__ rows_dev,
+                     int N, uint8_t* __restrict__ out) {
+    const int64_t n = (int64_t)__ldg(rows_dev) * N;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / N;
+        out[(int64_t)__ldg(tok_of_row + r) * N + (i - r * N)] = rows_gates[i];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // the policy head Dense(K, N <= 4) on fp16 pairs
 // ---------------------------------------------------------------------------------------------
 // logits[m][n] = (sum_k (H_hi + H_lo)[m][k] W[k][n]) / scale + b[n]: one warp per token row, two rows in flight.
@@ -869,7 +1022,10 @@ f16_colsum_fold_kernel(const float* __restrict__ part, int64_t rows, int N, int6
 template <int N>
 __global__ void __launch_bounds__(256)
 head_fwd16_kernel(const __half* __restrict__ H_hi, const __half* __restrict__ H_lo, const float* __restrict__ W,
-                  const float* __restrict__ bias, float* __restrict__ logits, int64_t M, int K, const float* sc_h) {
+                  const float* __restrict__ bias, float* __restrict__ logits, int64_t M, int K, const float* sc_h,
+                  const int* __restrict__ M_dev, const int* __restrict__ tok_of_row) {
+    // token compaction: H holds only the active tokens (*M_dev rows); row r is token tok_of_row[r] of the dense logits
+    if (M_dev != nullptr) M = min((int64_t)__ldg(M_dev), M);
     extern __shared__ __align__(16) float sW[];   // [8][N][K/8]
     const int KV = K >> 3;
     for (int i = threadIdx.x; i < K * N; i += blockDim.x) {
@@ -914,11 +1070,13 @@ head_fwd16_kernel(const __half* __restrict__ H_hi, const __half* __restrict__ H_
                 a1[n] += __shfl_xor_sync(0xffffffffu, a1[n], d);
             }
         if (lane == 0) {
+            const int64_t o0 = tok_of_row ? (int64_t)__ldg(tok_of_row + m) : m;
+            const int64_t o1 = (two && tok_of_row) ? (int64_t)__ldg(tok_of_row + m2) : m2;
 #pragma unroll
             for (int n = 0; n < N; ++n) {
                 const float bn = bias ? bias[n] : 0.0f;
-                logits[m * N + n] = fmaf(a0[n], inv, bn);
-                if (two) logits[m2 * N + n] = fmaf(a1[n], inv, bn);
+                logits[o0 * N + n] = fmaf(a0[n], inv, bn);
+                if (two) logits[o1 * N + n] = fmaf(a1[n], inv, bn);
             }
         }
     }
@@ -933,8 +1091,13 @@ __global__ void __launch_bounds__(256, 2)
 head_bwd16_kernel(const __half* __restrict__ H_hi, const __half* __restrict__ H_lo,
                   const float* __restrict__ dlogits, const float* __restrict__ W, __half* __restrict__ dH_hi, __half* __restrict__ dH_lo,
                   float* __restrict__ partial, int64_t M, int K, float slope, int64_t rows_per_cta, int need_dH,
-                  const float* sc_h, const float* sc_dh) {
+                  const float* sc_h, const float* sc_dh, const int* __restrict__ M_dev, const int* __restrict__ tok_of_row) {
     extern __shared__ float red[];                     // [rpp][K*N + N + K]
+    const int64_t M_alloc = M;
+    if (M_dev != nullptr) {      // token compaction: rows = active tokens, row r reads the dlogits of token tok_of_row[r]
+        M = min((int64_t)__ldg(M_dev), M);
+        rows_per_cta = (M + gridDim.x - 1) / gridDim.x;
+    }
     const int tid = threadIdx.x;
     const int TPR = K >> 2;
     const int rpp = 256 / TPR;
@@ -970,8 +1133,9 @@ head_bwd16_kernel(const __half* __restrict__ H_hi, const __half* __restrict__ H_
                 hh[u] = __ldcs(reinterpret_cast<const uint2*>(H_hi + row * K + k));
                 hl[u] = __ldcs(reinterpret_cast<const uint2*>(H_lo + row * K + k));
             }
+            const int64_t tok = (rv && tok_of_row != nullptr) ? (int64_t)__ldg(tok_of_row + row) : row;
 #pragma unroll
-            for (int n = 0; n < N; ++n) d[u][n] = rv ? __ldg(dlogits + row * N + n) : 0.0f;
+            for (int n = 0; n < N; ++n) d[u][n] = rv ? __ldg(dlogits + tok * N + n) : 0.0f;
         }
 #pragma unroll
         for (int u = 0; u < RU; ++u) {
@@ -1032,6 +1196,16 @@ head_bwd16_kernel(const __half* __restrict__ H_hi, const __half* __restrict__ H_
         float s = 0.0f;
         for (int g = 0; g < rpp; ++g) s += red[(size_t)g * stride + i];
         pw[i] = s;
+    }
+    // the wgrad contraction of the layer below reads dH in whole 128-row groups: zero the rows between the data and the
+    // next multiple of 128 (compaction leaves stale rows of an earlier, larger minibatch there)
+    if (need_dH && M_dev != nullptr && blockIdx.x == gridDim.x - 1) {
+        const int64_t end = min((M + 127) / 128 * 128, M_alloc);
+        const int64_t n4 = (end - M) * (int64_t)(K >> 2);
+        for (int64_t i = tid; i < n4; i += 256) {
+            *reinterpret_cast<uint2*>(dH_hi + M * K + 4 * i) = make_uint2(0u, 0u);
+            *reinterpret_cast<uint2*>(dH_lo + M * K + 4 * i) = make_uint2(0u, 0u);
+        }
     }
 }
 
@@ -1110,6 +1284,11 @@ struct F16State {
     size_t partial_bytes = 0;
     float* sc = nullptr;                     // scale pairs
     unsigned* st = nullptr;                  // [0] abs-max X0, [1] abs-max dlogits, [2 + 4 l + j] weight statistics
+    // token compaction (see token_compact_kernel)
+    int* tok_of_row = nullptr;               // [tokens] row -> token of the dense minibatch, ascending
+    int* blk_counts = nullptr;               // [ceil(tokens / TOK_PER_BLOCK)] active tokens per block
+    int* d_rows = nullptr;                   // number of active tokens of the current minibatch
+    bool compact = false;                    // the last forward pass ran compacted (the backward pass follows it)
 };
 
 F16State* state(ppo_policy* p) { return reinterpret_cast<F16State*>(p->f16); }
@@ -1227,14 +1406,14 @@ int kk16_dispatch(ppo_ctx* ctx, const __half* A, const __half* A_lo, const __hal
 
 template <int BN>
 int launch_mn16(ppo_ctx* ctx, const __half* X, const __half* X_lo, const __half* dY, const __half* dY_lo, int64_t M, int Kin,
-                int Nout, float* partial, int splits) {
+                int Nout, float* partial, int splits, const int* M_dev) {
     CUtensorMap mA, mAl, mB, mBl;
     PPO_TRY(make_map16_mn(&mA, X, M, Kin, F_BM / 64));
     PPO_TRY(make_map16_mn(&mAl, X_lo, M, Kin, F_BM / 64));
     PPO_TRY(make_map16_mn(&mB, dY, M, Nout, BN / 64));
     PPO_TRY(make_map16_mn(&mBl, dY_lo, M, Nout, BN / 64));
     MN16Params p;
-    p.Kin = Kin; p.Nout = Nout; p.M = M;
+    p.Kin = Kin; p.Nout = Nout; p.M = M; p.M_dev = M_dev;
     p.tiles_k = (int)ceil_div(Kin, F_BM); p.tiles_n = (int)ceil_div(Nout, BN); p.splits = splits;
     p.rows_per_split = round_up(ceil_div(M, splits), F_CHUNK_KB * F_BK);
     p.partial = partial;
@@ -1248,11 +1427,11 @@ int launch_mn16(ppo_ctx* ctx, const __half* X, const __half* X_lo, const __half*
 }
 
 // fold [rows][N] per-quarter column sums (rows = 4 * tiles_m) into out[N]; scratch holds 64 * N floats
-int fold_colsum16(ppo_ctx* ctx, const float* part, int64_t rows, int N, float* scratch, float* out) {
+int fold_colsum16(ppo_ctx* ctx, const float* part, int64_t rows, int N, float* scratch, float* out, const int* M_dev = nullptr) {
     const int chunks = (int)std::min<int64_t>(64, rows);
     const int64_t rpc = ceil_div(rows, chunks);
     dim3 grid((unsigned)ceil_div(N, 256), (unsigned)chunks);
-    f16_colsum_fold_kernel<<<grid, 256, 0, ctx->stream>>>(part, rows, N, rpc, scratch);
+    f16_colsum_fold_kernel<<<grid, 256, 0, ctx->stream>>>(part, rows, N, rpc, scratch, M_dev);
     f16_reduce_kernel<<<(unsigned)ceil_div(N, 256), 256, 0, ctx->stream>>>(scratch, chunks, N, N, out, nullptr, nullptr);
     ctx->launches += 2;
     PPO_CUDA(cudaGetLastError());
@@ -1260,14 +1439,15 @@ int fold_colsum16(ppo_ctx* ctx, const float* part, int64_t rows, int N, float* s
 }
 
 int wgrad16(ppo_ctx* ctx, const __half* X, const __half* X_lo, const __half* dY, const __half* dY_lo, float* dW,
-            float* partial, size_t partial_bytes, int64_t M, int K, int N, const float* sc_x, const float* sc_dy) {
+            float* partial, size_t partial_bytes, int64_t M, int K, int N, const float* sc_x, const float* sc_dy,
+            const int* M_dev = nullptr) {
     PPO_REQUIRE(K % 8 == 0 && N % 32 == 0, "f16 wgrad: K %% 8 and N %% 32 required (K=%d N=%d)", K, N);
     const int BN = N > 128 ? 256 : 128;
     const int tiles = (int)(ceil_div(K, F_BM) * ceil_div(N, BN));
     const int splits = wgrad_splits16(M, tiles, ctx->num_sms);
     PPO_REQUIRE((size_t)splits * K * N * 4 <= partial_bytes, "f16 wgrad: partial buffer too small");
-    if (BN == 256) PPO_TRY(launch_mn16<256>(ctx, X, X_lo, dY, dY_lo, M, K, N, partial, splits));
-    else PPO_TRY(launch_mn16<128>(ctx, X, X_lo, dY, dY_lo, M, K, N, partial, splits));
+    if (BN == 256) PPO_TRY(launch_mn16<256>(ctx, X, X_lo, dY, dY_lo, M, K, N, partial, splits, M_dev));
+    else PPO_TRY(launch_mn16<128>(ctx, X, X_lo, dY, dY_lo, M, K, N, partial, splits, M_dev));
     const int64_t cnt = (int64_t)K * N;
     f16_reduce_kernel<<<(unsigned)ceil_div(cnt, 256), 256, 0, ctx->stream>>>(partial, splits, cnt, cnt, dW, sc_x, sc_dy);
     ctx->launches += 1;
@@ -1276,17 +1456,17 @@ int wgrad16(ppo_ctx* ctx, const __half* X, const __half* X_lo, const __half* dY,
 }
 
 int head_fwd16(ppo_ctx* ctx, const __half* H_hi, const __half* H_lo, const float* W, const float* bias, float* logits,
-               int64_t M, int K, int N, const float* sc_h) {
+               int64_t M, int K, int N, const float* sc_h, const int* M_dev = nullptr, const int* tok_of_row = nullptr) {
     PPO_REQUIRE(N >= 1 && N <= 4 && K % 8 == 0 && (size_t)K * N * 4 <= 48 * 1024, "f16 head_fwd: needs N <= 4, K %% 8 == 0 (K=%d N=%d)", K, N);
     int64_t blocks = ceil_div(M, 8);
     const int64_t cap = (int64_t)ctx->num_sms * 8;
     if (blocks > cap) blocks = cap;
     const size_t smem = (size_t)K * N * sizeof(float);
     switch (N) {
-        case 1: head_fwd16_kernel<1><<<(unsigned)blocks, 256, smem, ctx->stream>>>(H_hi, H_lo, W, bias, logits, M, K, sc_h); break;
-        case 2: head_fwd16_kernel<2><<<(unsigned)blocks, 256, smem, ctx->stream>>>(H_hi, H_lo, W, bias, logits, M, K, sc_h); break;
-        case 3: head_fwd16_kernel<3><<<(unsigned)blocks, 256, smem, ctx->stream>>>(H_hi, H_lo, W, bias, logits, M, K, sc_h); break;
-        default: head_fwd16_kernel<4><<<(unsigned)blocks, 256, smem, ctx->stream>>>(H_hi, H_lo, W, bias, logits, M, K, sc_h); break;
+        case 1: head_fwd16_kernel<1><<<(unsigned)blocks, 256, smem, ctx->stream>>>(H_hi, H_lo, W, bias, logits, M, K, sc_h, M_dev, tok_of_row); break;
+        case 2: head_fwd16_kernel<2><<<(unsigned)blocks, 256, smem, ctx->stream>>>(H_hi, H_lo, W, bias, logits, M, K, sc_h, M_dev, tok_of_row); break;
+        case 3: head_fwd16_kernel<3><<<(unsigned)blocks, 256, smem, ctx->stream>>>(H_hi, H_lo, W, bias, logits, M, K, sc_h, M_dev, tok_of_row); break;
+        default: head_fwd16_kernel<4><<<(unsigned)blocks, 256, smem, ctx->stream>>>(H_hi, H_lo, W, bias, logits, M, K, sc_h, M_dev, tok_of_row); break;
     }
     ctx->launches += 1;
     PPO_CUDA(cudaGetLastError());
@@ -1295,7 +1475,8 @@ int head_fwd16(ppo_ctx* ctx, const __half* H_hi, const __half* H_lo, const float
 
 int head_bwd16(ppo_ctx* ctx, const __half* H_hi, const __half* H_lo, const float* dlogits, const float* W, __half* dH_hi,
                __half* dH_lo, float* dW, float* db, float* db_below, int64_t M, int K, int N, float slope, float* partial,
-               size_t partial_bytes, const float* sc_h, const float* sc_dh) {
+               size_t partial_bytes, const float* sc_h, const float* sc_dh, const int* M_dev = nullptr,
+               const int* tok_of_row = nullptr) {
     PPO_REQUIRE(N >= 1 && N <= 4 && K % 4 == 0 && K >= 4 && K <= 1024, "f16 head_bwd: needs N <= 4, K %% 4 == 0, K <= 1024 (K=%d N=%d)", K, N);
     const int64_t ctas = head16_ctas(M, ctx->num_sms);
     const int64_t rows = ceil_div(M, ctas);
@@ -1305,10 +1486,10 @@ int head_bwd16(ppo_ctx* ctx, const __half* H_hi, const __half* H_lo, const float
     const int rpp = 256 / (K / 4);
     const size_t smem = (size_t)rpp * stride * sizeof(float);
     switch (N) {
-        case 1: head_bwd16_kernel<1><<<(unsigned)ctas, 256, smem, ctx->stream>>>(H_hi, H_lo, dlogits, W, dH_hi, dH_lo, partial, M, K, slope, rows, need_dH, sc_h, sc_dh); break;
-        case 2: head_bwd16_kernel<2><<<(unsigned)ctas, 256, smem, ctx->stream>>>(H_hi, H_lo, dlogits, W, dH_hi, dH_lo, partial, M, K, slope, rows, need_dH, sc_h, sc_dh); break;
-        case 3: head_bwd16_kernel<3><<<(unsigned)ctas, 256, smem, ctx->stream>>>(H_hi, H_lo, dlogits, W, dH_hi, dH_lo, partial, M, K, slope, rows, need_dH, sc_h, sc_dh); break;
-        default: head_bwd16_kernel<4><<<(unsigned)ctas, 256, smem, ctx->stream>>>(H_hi, H_lo, dlogits, W, dH_hi, dH_lo, partial, M, K, slope, rows, need_dH, sc_h, sc_dh); break;
+        case 1: head_bwd16_kernel<1><<<(unsigned)ctas, 256, smem, ctx->stream>>>(H_hi, H_lo, dlogits, W, dH_hi, dH_lo, partial, M, K, slope, rows, need_dH, sc_h, sc_dh, M_dev, tok_of_row); break;
+        case 2: head_bwd16_kernel<2><<<(unsigned)ctas, 256, smem, ctx->stream>>>(H_hi, H_lo, dlogits, W, dH_hi, dH_lo, partial, M, K, slope, rows, need_dH, sc_h, sc_dh, M_dev, tok_of_row); break;
+        case 3: head_bwd16_kernel<3><<<(unsigned)ctas, 256, smem, ctx->stream>>>(H_hi, H_lo, dlogits, W, dH_hi, dH_lo, partial, M, K, slope, rows, need_dH, sc_h, sc_dh, M_dev, tok_of_row); break;
+        default: head_bwd16_kernel<4><<<(unsigned)ctas, 256, smem, ctx->stream>>>(H_hi, H_lo, dlogits, W, dH_hi, dH_lo, partial, M, K, slope, rows, need_dH, sc_h, sc_dh, M_dev, tok_of_row); break;
     }
     ctx->launches += 1;
     PPO_CUDA(cudaGetLastError());
@@ -1332,6 +1513,7 @@ int ensure_f16_workspace(ppo_policy* p, int64_t tokens) {
     ppo_ctx* ctx = p->ctx;
     PPO_CUDA(cudaStreamSynchronize(ctx->stream));
     fr(st->x_hi); fr(st->x_lo); fr(st->dz_hi[0]); fr(st->dz_hi[1]); fr(st->dz_lo[0]); fr(st->dz_lo[1]); fr(st->partial);
+    fr(st->tok_of_row); fr(st->blk_counts);
     for (auto& a : st->act_hi) fr(a);
     for (auto& a : st->act_lo) fr(a);
     for (auto& a : st->act_sign) fr(a);
@@ -1341,19 +1523,29 @@ int ensure_f16_workspace(ppo_policy* p, int64_t tokens) {
     st->act_hi.assign(L + 1, nullptr);
     st->act_lo.assign(L + 1, nullptr);
     st->act_sign.assign(L + 1, nullptr);
-    // +256 B of slack: the MN-major 3-D view reads whole 64-column blocks of the last row
+    // +256 B of slack: the MN-major 3-D view reads whole 64-column blocks of the last row.  Every operand buffer starts
+    // out as zeros: with token compaction the kernels read whole 64 / 128-row blocks past the active rows, and what they
+    // find there (zeros, or finite values of an earlier minibatch) is multiplied by exact zeros.
     const size_t slack = 256;
-    PPO_CUDA(cudaMalloc((void**)&st->x_hi, (size_t)tokens * p->dims[0] * 2 + slack));
-    PPO_CUDA(cudaMalloc((void**)&st->x_lo, (size_t)tokens * p->dims[0] * 2 + slack));
+    auto zalloc = [&](__half** q, size_t bytes) -> int {
+        PPO_CUDA(cudaMalloc((void**)q, bytes));
+        PPO_CUDA(cudaMemsetAsync(*q, 0, bytes, ctx->stream));
+        return PPO_OK;
+    };
+    PPO_TRY(zalloc(&st->x_hi, (size_t)tokens * p->dims[0] * 2 + slack));
+    PPO_TRY(zalloc(&st->x_lo, (size_t)tokens * p->dims[0] * 2 + slack));
     for (int l = 1; l < L; ++l) {
-        PPO_CUDA(cudaMalloc((void**)&st->act_hi[l], (size_t)tokens * p->dims[l] * 2 + slack));
-        PPO_CUDA(cudaMalloc((void**)&st->act_lo[l], (size_t)tokens * p->dims[l] * 2 + slack));
+        PPO_TRY(zalloc(&st->act_hi[l], (size_t)tokens * p->dims[l] * 2 + slack));
+        PPO_TRY(zalloc(&st->act_lo[l], (size_t)tokens * p->dims[l] * 2 + slack));
         if (l < L - 1) PPO_CUDA(cudaMalloc((void**)&st->act_sign[l], sign_words(tokens, p->dims[l]) * 4));   // (the head gates on sign(hi))
     }
     for (int i = 0; i < 2; ++i) {
-        PPO_CUDA(cudaMalloc((void**)&st->dz_hi[i], (size_t)tokens * hmax * 2 + slack));
-        PPO_CUDA(cudaMalloc((void**)&st->dz_lo[i], (size_t)tokens * hmax * 2 + slack));
+        PPO_TRY(zalloc(&st->dz_hi[i], (size_t)tokens * hmax * 2 + slack));
+        PPO_TRY(zalloc(&st->dz_lo[i], (size_t)tokens * hmax * 2 + slack));
     }
+    PPO_CUDA(cudaMalloc((void**)&st->tok_of_row, (size_t)tokens * sizeof(int)));
+    PPO_CUDA(cudaMalloc((void**)&st->blk_counts, (size_t)ceil_div(tokens, TOK_PER_BLOCK) * sizeof(int)));
+    if (st->d_rows == nullptr) PPO_CUDA(cudaMalloc((void**)&st->d_rows, sizeof(int)));
     size_t pb = 16;
     for (int l = 0; l + 1 < L; ++l) pb = std::max(pb, f16_partial_bytes(tokens, p->dims[l], p->dims[l + 1], ctx->num_sms));
     pb = std::max(pb, head16_partial_bytes(tokens, p->dims[L - 1], p->dims[L], ctx->num_sms));
@@ -1433,29 +1625,47 @@ int f16_refresh_weights(ppo_policy* p) {
     return PPO_OK;
 }
 
-int f16_forward(ppo_policy* p, const float* X, int64_t M) {
+int f16_forward(ppo_policy* p, const float* X, int64_t M, const float* mask) {
     F16State* st = state(p);
     PPO_REQUIRE(st != nullptr, "fp16-split engine not prepared");
     ppo_ctx* ctx = p->ctx;
     const int L = p->L;
     PPO_TRY(ensure_f16_workspace(p, p->ws_tokens > M ? p->ws_tokens : M));
-    PPO_TRY(launch_absmax(ctx, X, M * p->dims[0], st->st + 0));
+    PPO_TRY(launch_absmax(ctx, X, M * p->dims[0], st->st + 0));      // over all tokens: a bound is all the plan needs
     plan_fwd_kernel<<<1, 32, 0, ctx->stream>>>(L, p->slope, st->st + 0, st->st + 2, st->sc);
     ctx->launches += 1;
-    PPO_TRY(launch_split16(ctx, X, st->x_hi, st->x_lo, M * p->dims[0], st->sc + 2 * sc_act(0)));
+    // token compaction (mask: the minibatch's [rows][nhe * apa] action mask, or nullptr = run every token)
+    st->compact = mask != nullptr && p->compact_tokens != 0 && M >= 1;
+    const int* M_dev = st->compact ? st->d_rows : nullptr;
+    const int* tok = st->compact ? st->tok_of_row : nullptr;
+    if (st->compact) {
+        const int apa = p->dims[L];
+        const unsigned nblk = (unsigned)ceil_div(M, TOK_PER_BLOCK);
+        token_count_kernel<<<nblk, TOK_THREADS, 0, ctx->stream>>>(mask, M, apa, st->blk_counts);
+        token_compact_kernel<<<nblk, TOK_THREADS, 0, ctx->stream>>>(mask, M, apa, st->blk_counts, st->tok_of_row, st->d_rows);
+        const int K8 = p->dims[0] / 8;
+        const int64_t blocks = std::max<int64_t>(1, std::min<int64_t>(ceil_div(M * K8, 256), (int64_t)ctx->num_sms * 16));
+        split16_rows_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(X, tok, M_dev, K8, st->x_hi, st->x_lo, st->sc + 2 * sc_act(0), M);
+        ctx->launches += 3;
+        PPO_CUDA(cudaGetLastError());
+    } else {
+        PPO_TRY(launch_split16(ctx, X, st->x_hi, st->x_lo, M * p->dims[0], st->sc + 2 * sc_act(0)));
+    }
     for (int l = 0; l + 1 < L; ++l) {
         const int K = p->dims[l], N = p->dims[l + 1];
         F16Layer& ly = st->layers[l];
         KK16Params kp{};
         kp.epi = F_EPI_FWD; kp.act = 1; kp.slope = p->slope; kp.bias = p->params + p->b_off[l];
+        kp.M_dev = M_dev;
         kp.sc_a = st->sc + 2 * sc_act(l); kp.sc_b = st->sc + 2 * sc_w(L, l); kp.sc_c = st->sc + 2 * sc_act(l + 1);
         const __half* A_hi = (l == 0) ? st->x_hi : st->act_hi[l];
         const __half* A_lo = (l == 0) ? st->x_lo : st->act_lo[l];
         kp.signs_out = st->act_sign[l + 1];      // nullptr for the last hidden layer
         PPO_TRY(kk16_dispatch(ctx, A_hi, A_lo, ly.WT_hi, ly.WT_lo, st->act_hi[l + 1], st->act_lo[l + 1], M, N, K, kp));
     }
+    // (compacted: the logits of skipped tokens keep whatever finite value they held; the mask turns them into -Inf)
     return head_fwd16(ctx, st->act_hi[L - 1], st->act_lo[L - 1], p->params + p->w_off[L - 1], p->params + p->b_off[L - 1],
-                      p->act[L], M, p->dims[L - 1], p->dims[L], st->sc + 2 * sc_act(L - 1));
+                      p->act[L], M, p->dims[L - 1], p->dims[L], st->sc + 2 * sc_act(L - 1), M_dev, tok);
 }
 
 int f16_backward(ppo_policy* p, int64_t M) {
@@ -1464,6 +1674,8 @@ int f16_backward(ppo_policy* p, int64_t M) {
     ppo_ctx* ctx = p->ctx;
     const int L = p->L;
     PPO_REQUIRE(M <= st->tokens, "fp16-split engine: backward without a forward of the same minibatch");
+    const int* M_dev = st->compact ? st->d_rows : nullptr;
+    const int* tok = st->compact ? st->tok_of_row : nullptr;
     PPO_TRY(launch_absmax(ctx, p->dlogits, M * p->dims[L], st->st + 1));
     plan_bwd_kernel<<<1, 32, 0, ctx->stream>>>(L, p->slope, st->st + 1, st->st + 2, st->sc);
     ctx->launches += 1;
@@ -1472,7 +1684,7 @@ int f16_backward(ppo_policy* p, int64_t M) {
     PPO_TRY(head_bwd16(ctx, st->act_hi[L - 1], st->act_lo[L - 1], p->dlogits, p->params + p->w_off[L - 1], st->dz_hi[pp],
                        st->dz_lo[pp], p->grads + p->w_off[L - 1], p->grads + p->b_off[L - 1], p->grads + p->b_off[L - 2], M,
                        p->dims[L - 1], p->dims[L], p->slope, st->partial, st->partial_bytes, st->sc + 2 * sc_act(L - 1),
-                       st->sc + 2 * sc_dz(L, L - 2)));
+                       st->sc + 2 * sc_dz(L, L - 2), M_dev, tok));
     // data parallelism: a layer's slice of the flat gradient vector (dW_l, db_l: contiguous in Flux.params order) is
     // all-reduced on the communication stream as soon as it is complete, while the layers below still compute
     PPO_TRY(grads_ready(ctx, p->grads + p->w_off[L - 1], p->P - p->w_off[L - 1]));
@@ -1483,17 +1695,18 @@ int f16_backward(ppo_policy* p, int64_t M) {
         const __half* X_lo = (l == 0) ? st->x_lo : st->act_lo[l];
         const float* sc_dy = st->sc + 2 * sc_dz(L, l);
         PPO_TRY(wgrad16(ctx, X_hi, X_lo, st->dz_hi[pp], st->dz_lo[pp], p->grads + p->w_off[l], st->partial, st->partial_bytes, M,
-                        K, N, st->sc + 2 * sc_act(l), sc_dy));
+                        K, N, st->sc + 2 * sc_act(l), sc_dy, M_dev));
         PPO_TRY(grads_ready(ctx, p->grads + p->w_off[l], p->w_off[l + 1] - p->w_off[l]));      // dW_l and db_l (db_l came from above)
         if (l > 0) {
             KK16Params kp{};
             kp.epi = F_EPI_DGRAD; kp.act = 0; kp.slope = p->slope; kp.gate = st->act_sign[l];
             kp.colsum_partial = st->partial;
+            kp.M_dev = M_dev;
             kp.sc_a = sc_dy; kp.sc_b = st->sc + 2 * sc_w(L, l); kp.sc_c = st->sc + 2 * sc_dz(L, l - 1);
             // dX[M, K] = dY[M, N] * W[K, N]^T : A = dY (K-major in N), B = W rows (K-major in N)
             PPO_TRY(kk16_dispatch(ctx, st->dz_hi[pp], st->dz_lo[pp], ly.W_hi, ly.W_lo, st->dz_hi[pp ^ 1], st->dz_lo[pp ^ 1], M, K, N, kp));
             const int64_t rows = 4 * ceil_div(M, F_BM);
-            PPO_TRY(fold_colsum16(ctx, st->partial, rows, K, st->partial + (size_t)rows * K, p->grads + p->b_off[l - 1]));
+            PPO_TRY(fold_colsum16(ctx, st->partial, rows, K, st->partial + (size_t)rows * K, p->grads + p->b_off[l - 1], M_dev));
             pp ^= 1;
         }
     }
@@ -1508,10 +1721,31 @@ int f16_read_gates(ppo_policy* p, int l, int64_t M, uint8_t* d_out) {
     const int N = p->dims[l];
     const int64_t n = M * N;
     const unsigned blocks = (unsigned)std::min<int64_t>(ceil_div(n, 256), (int64_t)ctx->num_sms * 16);
-    if (l < p->L - 1) gates_from_signbits_kernel<<<blocks, 256, 0, ctx->stream>>>(st->act_sign[l], M, N, d_out);
-    else gates_from_hi_kernel<<<blocks, 256, 0, ctx->stream>>>(st->act_hi[l], n, d_out);
+    uint8_t* rows_out = d_out;
+    if (st->compact) {      // gates of the compacted rows go through the (idle) gradient ping-pong buffer, then to token order
+        rows_out = reinterpret_cast<uint8_t*>(st->dz_hi[0]);
+        PPO_CUDA(cudaMemsetAsync(d_out, PPO_GATE_SKIPPED, (size_t)n, ctx->stream));
+    }
+    if (l < p->L - 1) gates_from_signbits_kernel<<<blocks, 256, 0, ctx->stream>>>(st->act_sign[l], M, N, rows_out);
+    else gates_from_hi_kernel<<<blocks, 256, 0, ctx->stream>>>(st->act_hi[l], n, rows_out);
     ctx->launches += 1;
+    if (st->compact) {
+        gates_scatter_kernel<<<blocks, 256, 0, ctx->stream>>>(rows_out, st->tok_of_row, st->d_rows, N, d_out);
+        ctx->launches += 1;
+    }
     PPO_CUDA(cudaGetLastError());
+    return PPO_OK;
+}
+
+// active tokens of the last forward pass (-1: it ran every token)
+int f16_active_tokens(ppo_policy* p, int64_t* out) {
+    F16State* st = state(p);
+    *out = -1;
+    if (st == nullptr || !st->compact) return PPO_OK;
+    int v = 0;
+    PPO_CUDA(cudaMemcpyAsync(&v, st->d_rows, sizeof(int), cudaMemcpyDeviceToHost, p->ctx->stream));
+    PPO_CUDA(cudaStreamSynchronize(p->ctx->stream));
+    *out = v;
     return PPO_OK;
 }
 
@@ -1523,7 +1757,7 @@ void f16_destroy(ppo_policy* p) {
     for (auto& a : st->act_hi) fr(a);
     for (auto& a : st->act_lo) fr(a);
     for (auto& a : st->act_sign) fr(a);
-    fr(st->sc); fr(st->st);
+    fr(st->sc); fr(st->st); fr(st->tok_of_row); fr(st->blk_counts); fr(st->d_rows);
     delete st;
     p->f16 = nullptr;
 }

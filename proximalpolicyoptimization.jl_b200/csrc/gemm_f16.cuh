@@ -10,12 +10,16 @@ namespace ppo {
 int f16_prepare(ppo_policy* p);
 // weight statistics (abs-max, max column / row abs-sums) -> scales -> fp16 hi/lo copies of W and W^T
 int f16_refresh_weights(ppo_policy* p);
-// whole-MLP forward: X fp32 [M][dims[0]] -> p->act[L] (fp32 logits); hidden activations stay fp16 hi/lo pairs
-int f16_forward(ppo_policy* p, const float* X, int64_t M);
+// whole-MLP forward: X fp32 [M][dims[0]] -> p->act[L] (fp32 logits); hidden activations stay fp16 hi/lo pairs.
+// mask (optional): the minibatch's action mask [M * apa]; with p->compact_tokens the MLP then runs only on the tokens
+// that have at least one unmasked action (the logits of the others never reach the loss: softmax(-Inf) = 0)
+int f16_forward(ppo_policy* p, const float* X, int64_t M, const float* mask);
 // whole-MLP backward from p->dlogits -> p->grads
 int f16_backward(ppo_policy* p, int64_t M);
 // the leakyrelu' gates of hidden activation l (1..L-1) as the backward pass of the last minibatch applies them
+// (tokens the compacted MLP skipped: PPO_GATE_SKIPPED)
 int f16_read_gates(ppo_policy* p, int l, int64_t M, uint8_t* d_out);
+int f16_active_tokens(ppo_policy* p, int64_t* out);
 void f16_destroy(ppo_policy* p);
 
 // ---- stand-alone entry points on device pointers (ppo_dense_op / ppo_bench_kernel) ----

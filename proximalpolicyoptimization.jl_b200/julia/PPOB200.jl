@@ -163,6 +163,14 @@ dense_layers(model) = [l for l in model.layers if l isa Dense]
 # gemm_mode: -1 = auto (fastest fp32-parity engine whose shape contract the model meets), 0 = fp32 FFMA, 1 = 3xTF32
 # tcgen05, 3 = scaled fp16 hi/lo pairs on tcgen05 (needs in % 8 == 0, hidden widths % 32 == 0, <= 4 actions per token)
 gemm_mode(p) = ccall((:ppo_policy_get_gemm_mode, lib), Cint, (Ptr{Cvoid},), p.h)
+# token compaction (default on): the MLP skips tokens all of whose actions are masked (-Inf32); their probabilities
+# and gradients are exactly 0 either way
+token_compaction!(p, enable::Bool) = check(ccall((:ppo_policy_set_token_compaction, lib), Cint, (Ptr{Cvoid}, Cint), p.h, enable ? 1 : 0))
+function active_tokens(p)
+    r = Ref{Int64}(-1)
+    check(ccall((:ppo_policy_active_tokens, lib), Cint, (Ptr{Cvoid}, Ref{Int64}), p.h, r))
+    r[]
+end
 function DevicePolicy(ctx::Context, model; leaky_slope = 0.01f0, gemm_mode = -1)
     ls = dense_layers(model)
     dims = Cint[size(ls[1].weight, 2); [size(l.weight, 1) for l in ls]]

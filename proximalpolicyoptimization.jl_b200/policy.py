@@ -93,6 +93,18 @@ class Policy:
         _lib.check(_lib.load().ppo_policy_read_gates(self.handle, int(layer), int(rows), _lib.ptr(out, C.c_uint8)))
         return out
 
+    def set_token_compaction(self, enable: bool):
+        """fp16-split engine: run the MLP only on tokens with at least one unmasked action (default on).  Fully masked
+        tokens have probability exactly 0 and gradient exactly 0, so losses / probabilities / gradients are those of
+        the dense evaluation (up to the weight gradient's summation order)."""
+        _lib.check(_lib.load().ppo_policy_set_token_compaction(self.handle, 1 if enable else 0))
+
+    def active_tokens(self) -> int:
+        """tokens the last forward pass ran; -1 when it ran every token of the minibatch"""
+        out = C.c_int64(-1)
+        _lib.check(_lib.load().ppo_policy_active_tokens(self.handle, C.byref(out)))
+        return int(out.value)
+
     def p2p_export(self) -> bytes:
         buf = C.create_string_buffer(64)
         _lib.check(_lib.load().ppo_policy_p2p_export(self.handle, buf))

@@ -74,13 +74,22 @@ def _old_probs(o64, rng, feat, mask, act, chunk=8192):
     return (sel * np.exp(rng.normal(0, 0.1, nb))).clip(1e-6, 1).astype(np.float32)
 
 
-def _check_gate_disagreements(acts, gates, slope, tag):
-    """every device branch that differs from the oracle's own sits at a ~0 pre-activation"""
+SKIPPED = 255      # PPO_GATE_SKIPPED: a token the compacted MLP did not run
+
+
+def _check_gate_disagreements(acts, gates, slope, tag, mask=None, apa=None):
+    """every device branch that differs from the oracle's own sits at a ~0 pre-activation; the tokens a compacted pass
+    skipped are exactly the tokens all of whose actions are masked (their incoming gradient is an exact zero)"""
     flips = []
     for l, g in gates.items():
         a = acts[l]
         z = np.where(a > 0, a, a / slope)               # Float64 pre-activation of hidden layer l
-        diff = g.astype(bool) != (a > 0)
+        skipped = g == SKIPPED
+        if mask is not None:
+            dead = np.all(np.isneginf(mask.reshape(-1, apa)), axis=1)
+            assert np.array_equal(skipped.all(axis=1), skipped.any(axis=1)), (tag, l)
+            assert np.array_equal(skipped.all(axis=1), dead) or not skipped.any(), (tag, l)
+        diff = (g.astype(bool) != (a > 0)) & ~skipped
         n = int(diff.sum())
         flips.append(n)
         if n:
@@ -89,30 +98,38 @@ def _check_gate_disagreements(acts, gates, slope, tag):
     return flips
 
 
-def _device_vs_oracle(ctx, cfg, mode, seed, nb):
+def _device_vs_oracle(ctx, cfg, mode, seed, nb, compact=True):
     rng, feat, mask, act, W, b, adv = _case(cfg, nb, seed)
     o64 = _oracle64(cfg, W, b)
     old = _old_probs(o64, rng, feat, mask, act)
     pol = P.Policy(cfg.nf, cfg.H, cfg.L, cfg.apa, ctx, weights=W, biases=b, gemm_mode=mode)
     assert pol.gemm_mode == mode
+    pol.set_token_compaction(compact)
     lin = P.get_linear_action_index(act, cfg.A)
     gp, ge, grads = P.step_batch_(pol, None, P.StateData(feat, mask), lin, old, adv, EPS, W_ENT, return_grads=True)
     M = nb * cfg.nhe
     gates = {l: pol.read_gates(l, M) for l in range(1, cfg.L + 1)}
+    live = int((~np.all(np.isneginf(mask.reshape(-1, cfg.apa)), axis=1)).sum())
+    assert pol.active_tokens() == (live if (compact and mode == F16) else -1), (pol.active_tokens(), live, M)
+    assert (gates[1] == SKIPPED).any() == (compact and mode == F16 and live < M)
     pol.close()
     pl, ew, dW, db, acts = O.policy_gradient(o64, feat.astype(np.float64), mask.astype(np.float64), act,
                                              old.astype(np.float64), adv.astype(np.float64), EPS, W_ENT,
                                              gates=gates, return_acts=True)
-    flips = _check_gate_disagreements(acts, gates, 0.01, (mode, seed))
+    flips = _check_gate_disagreements(acts, gates, 0.01, (mode, seed), mask, cfg.apa)
     errs = _tensor_errors(cfg.dims, grads, _flat(dW, db))
     return (gp, ge), (pl, ew), errs, flips
 
 
+@pytest.mark.parametrize("compact", [True, False], ids=["compact", "dense"])
 @pytest.mark.parametrize("seed", range(24))
-def test_f16_engine_gradient_vs_fp64_oracle(ctx, seed):
-    """the engine every bench number rides on, 24 seeds, MLP 3x512 on 64 features x 16 tokens, 512 samples"""
+def test_f16_engine_gradient_vs_fp64_oracle(ctx, seed, compact):
+    """the engine every bench number rides on, 24 seeds, MLP 3x512 on 64 features x 16 tokens, 512 samples; with token
+    compaction (the default: ~19 % of these tokens are fully masked and skipped) and with every token run"""
+    if not compact and seed >= 6:
+        pytest.skip("dense evaluation: 6 seeds")
     cfg = S.CONFIGS["c3"]
-    (gp, ge), (pl, ew), errs, flips = _device_vs_oracle(ctx, cfg, F16, seed, 512)
+    (gp, ge), (pl, ew), errs, flips = _device_vs_oracle(ctx, cfg, F16, seed, 512, compact)
     assert abs(gp - pl) <= 1e-5 * abs(pl) + 1e-7, (seed, gp, pl)
     assert abs(ge - ew) <= 1e-5 * abs(ew) + 1e-8, (seed, ge, ew)
     assert max(errs) <= 1e-5, (seed, errs, flips)
@@ -171,6 +188,8 @@ def test_f16_engine_full_c3_minibatch_vs_fp64_oracle(ctx):
                                   EPS, W_ENT, return_grads=True)
     M = nb * cfg.nhe
     gates = {l: pol.read_gates(l, M) for l in range(1, cfg.L + 1)}
+    live = int((~np.all(np.isneginf(mask.reshape(-1, cfg.apa)), axis=1)).sum())
+    assert pol.active_tokens() == live and live < M          # token compaction is on by default
     pol.close()
     chunk = 4096
     want = np.zeros(cfg.num_params)
@@ -183,7 +202,7 @@ def test_f16_engine_full_c3_minibatch_vs_fp64_oracle(ctx):
         p_, e_, dW, db, acts = O.policy_gradient(o64, feat[s:e].astype(np.float64), mask[s:e].astype(np.float64), act[s:e],
                                                  old[s:e].astype(np.float64), adv[s:e].astype(np.float64), EPS, W_ENT,
                                                  gates=g, nb_total=nb, return_acts=True)
-        flips += np.array(_check_gate_disagreements(acts, g, 0.01, ("full", s)))
+        flips += np.array(_check_gate_disagreements(acts, g, 0.01, ("full", s), mask[s:e], cfg.apa))
         want += _flat(dW, db)
         pl += p_ * (e - s) / nb
         ew += e_ * (e - s) / nb

@@ -428,8 +428,10 @@ def test_error_behaviour(ctx):
     ds = P.construct_dataset(buf)
     with pytest.raises(P.PPOError):      # index outside 1..length
         ds[np.array([0, 1])]
-    with pytest.raises(AssertionError):
-        ds[4]
+    assert ds[4]["selected_action"] == 1
+    for bad in (0, 10):                      # @assert 1 <= idx <= length, src/rollout_buffer.jl:105-106
+        with pytest.raises(AssertionError):
+            ds[bad]
     with pytest.raises(TypeError):
         ds["x"]
     buf.close()

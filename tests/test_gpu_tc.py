@@ -187,3 +187,81 @@ def test_gemm_auto_picks_the_fastest_engine_inside_its_contract(ctx):
         assert pol.set_gemm_mode(SIMT) == SIMT
         assert pol.set_gemm_mode(P.GEMM_AUTO) == want, key
         pol.close()
+
+
+def _compaction_case(cfg, nb, seed, live_fraction):
+    """a minibatch whose tokens are fully masked (all apa actions -Inf) with probability 1 - live_fraction, token 0 of
+    every state alive (a state needs one legal action); live tokens carry per-action masks too"""
+    rng = np.random.default_rng(seed)
+    feat = rng.integers(-3, 9, (nb, cfg.nhe, cfg.nf)).astype(np.float32)
+    live = rng.random((nb, cfg.nhe)) < live_fraction
+    live[:, 0] = True
+    am = np.where(rng.random((nb, cfg.nhe, cfg.apa)) < 0.2, -np.inf, 0.0)
+    am[:, 0, 0] = 0.0
+    mask = np.where(live[:, :, None], am, -np.inf).astype(np.float32).reshape(nb, cfg.A)
+    act = S.make_actions(rng, mask)
+    W, b = S.make_weights(cfg)
+    b = [(x + rng.normal(0, 0.05, x.shape)).astype(np.float32) for x in b]
+    adv = rng.integers(-4, 5, nb).astype(np.float32)
+    old = rng.uniform(0.02, 0.9, nb).astype(np.float32)
+    return feat, mask, act, W, b, adv, old
+
+
+@pytest.mark.parametrize("key,nb,live", [("c3", 512, 0.8), ("c3", 512, 0.05), ("c3", 300, 1.0), ("c3", 7, 0.1),
+                                         ("c2", 64, 0.3), ("t2", 1000, 0.5)])
+def test_token_compaction_matches_the_dense_evaluation(ctx, key, nb, live):
+    """Token compaction (fp16-split engine, default on) runs the MLP only on tokens with an unmasked action.  Fully
+    masked tokens have probability exactly 0 and dlogits exactly 0, so against the same engine run on every token:
+    probabilities and losses are BIT-IDENTICAL (a row's logits do not depend on which tile it sits in), gradients agree
+    to summation order (1e-5 of every tensor's max-abs is the parity bound; here they are ~1e-6), and the run count
+    equals the number of live tokens -- from a mostly padded minibatch (5 % live, fewer rows than one 128-row tile) to
+    one with nothing to skip."""
+    cfg = S.CONFIGS[key]
+    feat, mask, act, W, b, adv, old = _compaction_case(cfg, nb, 11 + nb, live)
+    lin = P.get_linear_action_index(act, cfg.A)
+    n_live = int((~np.all(np.isneginf(mask.reshape(-1, cfg.apa)), axis=1)).sum())
+    out = {}
+    for compact in (False, True):
+        pol = P.Policy(cfg.nf, cfg.H, cfg.L, cfg.apa, ctx, weights=W, biases=b, gemm_mode=F16)
+        pol.set_token_compaction(compact)
+        probs = P.batch_action_probabilities(pol, P.StateData(feat, mask))
+        assert pol.active_tokens() == (n_live if compact else -1)
+        gp, ge, grads = P.step_batch_(pol, None, P.StateData(feat, mask), lin, old, adv, 0.05, 0.01, return_grads=True)
+        out[compact] = (probs, gp, ge, grads)
+        pol.close()
+    np.testing.assert_array_equal(out[True][0], out[False][0])
+    assert np.all(out[True][0][np.isneginf(mask)] == 0.0)
+    assert out[True][1] == out[False][1] and out[True][2] == out[False][2]
+    off = 0
+    for i, o in zip(cfg.dims[:-1], cfg.dims[1:]):
+        for size in (i * o, o):
+            d, c = out[False][3][off:off + size], out[True][3][off:off + size]
+            assert np.max(np.abs(d - c)) <= 2e-6 * np.max(np.abs(d)) + 1e-12, (key, nb, live, off)
+            off += size
+
+
+def test_token_compaction_epoch_with_cuda_graph(ctx):
+    """a whole epoch (first minibatch eager, the rest replayed from the CUDA graph, ragged last minibatch): the number
+    of live tokens differs from minibatch to minibatch and is only known on the device; compacted and dense epochs end
+    in the same weights to Adam's step granularity and the same loss history to 1e-6"""
+    cfg = S.Config("c3-mini", 93, 9000, 64, 16, 4, 512, 3, 1024)
+    data = S.make_buffer(cfg)
+    W, b = S.make_weights(cfg)
+    out = {}
+    for compact in (False, True):
+        buf = P.DeviceRollouts(cfg.nf, cfg.nhe, cfg.apa, cfg.N, ctx)
+        old = np.full(cfg.N, 0.05, np.float32)
+        buf.append(data["feat"], data["mask"], old, data["action"], data["reward"], data["terminal"])
+        P.compute_state_value_(buf, 1.0)
+        pol = P.Policy(cfg.nf, cfg.H, cfg.L, cfg.apa, ctx, weights=W, biases=b, gemm_mode=F16)
+        pol.set_token_compaction(compact)
+        perm = np.random.default_rng(3).permutation(cfg.N) + 1
+        mp_, me_ = P.step_epoch_(pol, P.Adam(1e-4), P.construct_dataset(buf), 0.05, cfg.B, 0.01, perm=perm)
+        Wd, bd = pol.weights()
+        out[compact] = (mp_, me_, _flat(Wd, bd))
+        pol.close(); buf.close()
+    assert abs(out[True][0] - out[False][0]) <= 1e-6 * abs(out[False][0]) + 1e-9
+    assert abs(out[True][1] - out[False][1]) <= 1e-6 * abs(out[False][1]) + 1e-9
+    # Adam normalises every step to ~eta: entries whose gradient is at summation-noise level may step either way
+    dw = np.abs(out[True][2] - out[False][2])
+    assert np.mean(dw > 2e-6) <= 1e-3 and np.max(dw) <= 2 * 1e-4 * 9, (float(np.max(dw)), float(np.mean(dw > 2e-6)))
