@@ -358,6 +358,9 @@ def run_update_legs(h, cfg, B_local, gemm_mode, data, W, b, steps, warmup, feat_
     ms_step, clocks, launches = h.timed(resident_step, steps, warmup, f"{cfg.name} resident", sample_clocks)
     out = {"ms_step": ms_step, "clocks": clocks, "launches": launches, "engine": pol.gemm_mode,
            "nbatches": (cfg.N + B_local - 1) // B_local, "active_tokens_last_minibatch": pol.active_tokens()}
+    if h.use_p2p:
+        ns, waits = pol.p2p_wait(reset=True)
+        out["p2p_wait_us_per_minibatch"] = round(ns / max(1, waits) / 1e3, 2)
     if e2e:
         def e2e_step(i):
             fill()
@@ -648,7 +651,8 @@ def _run_ours(args):
         line = None
         if rank == 0:
             line = json.dumps({"profile_only": True, "value": value, "ms_per_step": main["ms_step"],
-                               "gpu_launches": main["launches"], "launches_total": h.ctx.launch_count()})
+                               "gpu_launches": main["launches"], "launches_total": h.ctx.launch_count(),
+                               "p2p_wait_us_per_minibatch": main.get("p2p_wait_us_per_minibatch")})
         h.barrier()
         h.ctx.close()
         return line
@@ -657,6 +661,8 @@ def _run_ours(args):
            "d2h_bytes_per_step": 16 * main["nbatches"], "ms_per_step": main["ms_e2e"], "steps": args.steps}
     # token compaction is the library default; the same steps with every token pushed through the MLP (what the
     # reference does with fully masked tokens) are timed beside it
+    if "p2p_wait_us_per_minibatch" in main:
+        config["p2p_wait_us_per_minibatch_rank0"] = main["p2p_wait_us_per_minibatch"]
     last_rows = (cfg.N - (main["nbatches"] - 1) * B_local) * cfg.nhe
     config["token_compaction"] = {
         "enabled": main["active_tokens_last_minibatch"] >= 0,

@@ -168,6 +168,10 @@ int ppo_policy_write(ppo_policy* p, const float* const* W, const float* const* b
 int ppo_policy_set_gemm_mode(ppo_policy* p, int mode);
 /* the engine in use (after PPO_GEMM_AUTO: the one that was picked) */
 int ppo_policy_get_gemm_mode(ppo_policy* p);
+/* diagnostic of the peer-memory exchange: total nanoseconds this rank's optimiser kernel spent waiting for its peers'
+ * gradients (clock skew between the GPUs + the peers' publish latency) and the number of waits (minibatches);
+ * reset != 0 clears the counters.  Zeros when the exchange is not connected.  Synchronises. */
+int ppo_policy_p2p_wait(ppo_policy* p, int64_t* total_ns, int64_t* waits, int reset);
 /* Token compaction (fp16-split engine; on by default).  A token all of whose actions carry a -Inf mask has probability
  * exactly 0 for each of them (softmax(logits .+ mask), test/quad_game_utilities.jl:73-79), so its logits never reach the
  * loss and its rows add exact zeros to every gradient.  With compaction the MLP runs on the remaining tokens only

@@ -67,6 +67,7 @@ SIGNATURES = {
     "ppo_policy_active_tokens": (c_int, [vp, PI64]),
     "ppo_policy_p2p_export": (c_int, [vp, vp]),
     "ppo_policy_p2p_connect": (c_int, [vp, c_int, c_int, vp]),
+    "ppo_policy_p2p_wait": (c_int, [vp, PI64, PI64, c_int]),
     "ppo_policy_num_params": (c_i64, [vp]),
     "ppo_batch_action_probabilities": (c_int, [vp, c_i64, c_int, PF, PF, PF]),
     "ppo_sample_actions": (c_int, [vp, c_i64, c_int, PF, PF, c_u64, PI64, PF, PF]),

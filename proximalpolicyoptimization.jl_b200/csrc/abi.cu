@@ -218,8 +218,11 @@ int policy_backward(ppo_policy* p, const float* X, int64_t M) {
 
 // One minibatch of the update on device-resident batch arrays.  Writes {ppoloss, entropyloss}
 // (unweighted) to p->d_loss_hist[2*slot..].
+// advance_step: the device minibatch counter, to be advanced once the minibatch is done (CUDA-graph replay); the
+// fp16-split engine's fused optimiser kernel does it, otherwise a one-thread kernel is appended here
 int step_core(ppo_policy* p, ppo_opt* opt, const ppo_batch& bt, int64_t nb, int nhe, double epsilon,
-              double entropy_weight, double inv_nb_global, int64_t slot, const int* d_step = nullptr) {
+              double entropy_weight, double inv_nb_global, int64_t slot, const int* d_step = nullptr,
+              int* advance_step = nullptr) {
     ppo_ctx* ctx = p->ctx;
     const int L = p->L;
     const int apa = p->dims[L];
@@ -232,10 +235,18 @@ int step_core(ppo_policy* p, ppo_opt* opt, const ppo_batch& bt, int64_t nb, int 
                         inv_nb_global, p->dlogits, p->d_loss_partials, p->d_loss_hist + (d_step ? 0 : 2 * slot), nullptr,
                         d_step));
     PPO_TRY(policy_backward(p, bt.feat, M));
+    // fp16-split engine: optimiser step, weight statistics, scales, operand copies and the minibatch counter in one launch
+    const bool fused = opt != nullptr && p->gemm_mode == PPO_GEMM_F16X3_TC;
     if (ctx->nccl_comm != nullptr && ctx->nranks > 1 && p2p_active(p)) {
         // gradient all-reduce over NVLink peer memory, fused into the Adam kernel (dp_p2p.cu)
+        if (fused) {
+            P2PView xv{};
+            PPO_TRY(p2p_publish(p, &xv));
+            return f16_adam_refresh(p, opt, &xv, advance_step);
+        }
         PPO_TRY(p2p_reduce_and_step(p, opt));
         if (opt != nullptr) PPO_TRY(refresh_engine_weights(p));
+        if (advance_step != nullptr) PPO_TRY(launch_step_advance(ctx, advance_step));
         return PPO_OK;
     }
     if (ctx->nccl_comm != nullptr && ctx->nranks > 1) {
@@ -244,11 +255,13 @@ int step_core(ppo_policy* p, ppo_opt* opt, const ppo_batch& bt, int64_t nb, int 
         if (p->gemm_mode == PPO_GEMM_F16X3_TC && dp_overlap(ctx)) PPO_TRY(grads_join(ctx));
         else PPO_TRY(nccl_allreduce_f32(ctx, p->grads, p->P));
     }
+    if (fused) return f16_adam_refresh(p, opt, nullptr, advance_step);
     if (opt != nullptr) {
         PPO_TRY(launch_adam(ctx, p->params, opt->m, opt->v, p->grads, p->P, opt->eta, opt->beta1, opt->beta2,
                             opt->eps, opt->d_bp, 1.0f));
         PPO_TRY(refresh_engine_weights(p));
     }
+    if (advance_step != nullptr) PPO_TRY(launch_step_advance(ctx, advance_step));
     return PPO_OK;
 }
 
@@ -907,6 +920,12 @@ int ppo_policy_p2p_connect(ppo_policy* p, int nranks, int rank, const void* hand
 
 int ppo_policy_get_gemm_mode(ppo_policy* p) { return p ? p->gemm_mode : PPO_ERR_INVALID; }
 
+int ppo_policy_p2p_wait(ppo_policy* p, int64_t* total_ns, int64_t* waits, int reset) {
+    PPO_REQUIRE(p != nullptr && total_ns != nullptr && waits != nullptr, "p2p_wait: null argument");
+    PPO_TRY(use(p->ctx));
+    return p2p_wait_stats(p, total_ns, waits, reset);
+}
+
 int ppo_policy_set_token_compaction(ppo_policy* p, int enable) {
     PPO_REQUIRE(p != nullptr, "set_token_compaction: null policy");
     p->compact_tokens = enable ? 1 : 0;
@@ -1224,8 +1243,8 @@ int ppo_step_epoch(ppo_policy* p, ppo_opt* opt, ppo_buf* buf, double epsilon, in
         PPO_CUDA(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
         int st = gather_into(buf, buf->batch, buf->perm, batch_size, 0, ctx->d_step, batch_size);
         if (st == PPO_OK)
-            st = step_core(p, opt, buf->batch, batch_size, buf->nhe, epsilon, entropy_weight, 1.0 / counts[0], 0, ctx->d_step);
-        if (st == PPO_OK) st = launch_step_advance(ctx, ctx->d_step);
+            st = step_core(p, opt, buf->batch, batch_size, buf->nhe, epsilon, entropy_weight, 1.0 / counts[0], 0, ctx->d_step,
+                           ctx->d_step);
         cudaError_t ce = cudaStreamEndCapture(ctx->stream, &graph);
         if (st != PPO_OK) { if (graph) cudaGraphDestroy(graph); return st; }
         PPO_CUDA(ce);

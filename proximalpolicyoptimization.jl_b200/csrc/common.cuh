@@ -243,11 +243,22 @@ int grads_join(ppo_ctx* ctx);
 int nccl_allreduce_f64(ppo_ctx* ctx, double* d_buf, int64_t n);
 
 // dp_p2p.cu: gradient all-reduce over NVLink peer memory fused into the Adam step (one process per GPU, CUDA IPC)
+// what a kernel needs to read the peers' published gradients (dp_p2p.cu)
+struct P2PView {
+    const float* const* peer_xchg;   // [nranks] exchange buffers (own entry = local)
+    int64_t Ppad;                    // floats per half of the double buffer
+    const unsigned* flags;           // [nranks] this rank's flag words (epoch + 1 once a peer has published)
+    unsigned* state;                 // [0] epoch, [1] publish block counter, [2] error flag
+    int nranks;
+};
 bool p2p_active(const ppo_policy* p);
+// publish p->grads to the peers (the first half of p2p_reduce_and_step) and describe where to read them
+int p2p_publish(ppo_policy* p, P2PView* view);
 int p2p_export(ppo_policy* p, void* handle64);
 int p2p_connect(ppo_policy* p, int nranks, int rank, const void* handles);
 int p2p_reduce_and_step(ppo_policy* p, ppo_opt* opt);
 int p2p_check(ppo_policy* p);
+int p2p_wait_stats(ppo_policy* p, int64_t* total_ns, int64_t* waits, int reset);
 void p2p_destroy(ppo_policy* p);
 
 // l2 flush helper

@@ -31,7 +31,7 @@ struct DpP2P {
     void* block = nullptr;             // one allocation (one IPC handle): [flags: 256 B][xchg: 2 x Ppad floats]
     unsigned* flags = nullptr;
     float* xchg = nullptr;
-    unsigned* d_epoch = nullptr;       // [0] epoch, [1] publish block counter, [2] error flag
+    unsigned* d_epoch = nullptr;       // [0] epoch, [1] publish block counter, [2] error flag, [4..7] wait ns / waits (u64 x 2)
     float** d_peer_xchg = nullptr;     // [nranks] device pointers (own entry = local)
     unsigned** d_peer_flags = nullptr;
     std::vector<void*> opened;
@@ -183,8 +183,7 @@ void p2p_destroy(ppo_policy* p) {
     p->dp = nullptr;
 }
 
-// all-reduce p->grads over the ranks and (opt != nullptr) apply Adam, in one pass over peer memory
-int p2p_reduce_and_step(ppo_policy* p, ppo_opt* opt) {
+int p2p_publish(ppo_policy* p, P2PView* view) {
     DpP2P* d = reinterpret_cast<DpP2P*>(p->dp);
     PPO_REQUIRE(d != nullptr && d->connected, "p2p gradient exchange is not connected");
     ppo_ctx* ctx = p->ctx;
@@ -193,6 +192,22 @@ int p2p_reduce_and_step(ppo_policy* p, ppo_opt* opt) {
     if (blocks < 1) blocks = 1;
     p2p_publish_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(p->grads, n, d->xchg, d->Ppad, d->d_epoch, d->d_peer_flags,
                                                                  d->nranks, d->rank);
+    ctx->launches += 1;
+    PPO_CUDA(cudaGetLastError());
+    if (view != nullptr) {
+        view->peer_xchg = d->d_peer_xchg; view->Ppad = d->Ppad; view->flags = d->flags; view->state = d->d_epoch;
+        view->nranks = d->nranks;
+    }
+    return PPO_OK;
+}
+
+// all-reduce p->grads over the ranks and (opt != nullptr) apply Adam, in one pass over peer memory
+int p2p_reduce_and_step(ppo_policy* p, ppo_opt* opt) {
+    DpP2P* d = reinterpret_cast<DpP2P*>(p->dp);
+    PPO_REQUIRE(d != nullptr && d->connected, "p2p gradient exchange is not connected");
+    ppo_ctx* ctx = p->ctx;
+    const int64_t n = p->P;
+    PPO_TRY(p2p_publish(p, nullptr));
     int64_t ablocks = std::min<int64_t>(ceil_div(n, 256), (int64_t)ctx->num_sms * 8);
     if (opt != nullptr) {
         p2p_adam_kernel<<<(unsigned)ablocks, 256, 0, ctx->stream>>>(p->params, opt->m, opt->v, n, opt->eta, opt->beta1, opt->beta2,
@@ -205,8 +220,21 @@ int p2p_reduce_and_step(ppo_policy* p, ppo_opt* opt) {
                                                                    p->grads);
         p2p_tick_kernel<<<1, 1, 0, ctx->stream>>>(d->d_epoch, nullptr, 0.0, 0.0);
     }
-    ctx->launches += 3;
+    ctx->launches += 2;
     PPO_CUDA(cudaGetLastError());
+    return PPO_OK;
+}
+
+// diagnostic: total time (ns) this rank's optimiser kernel waited for its peers' gradients, and the number of waits
+int p2p_wait_stats(ppo_policy* p, int64_t* total_ns, int64_t* waits, int reset) {
+    DpP2P* d = reinterpret_cast<DpP2P*>(p->dp);
+    *total_ns = 0; *waits = 0;
+    if (!d || !d->connected) return PPO_OK;
+    unsigned long long v[2] = {0, 0};
+    PPO_CUDA(cudaMemcpyAsync(v, d->d_epoch + 4, sizeof(v), cudaMemcpyDeviceToHost, p->ctx->stream));
+    PPO_CUDA(cudaStreamSynchronize(p->ctx->stream));
+    *total_ns = (int64_t)v[0]; *waits = (int64_t)v[1];
+    if (reset) PPO_CUDA(cudaMemsetAsync(d->d_epoch + 4, 0, 16, p->ctx->stream));
     return PPO_OK;
 }
 

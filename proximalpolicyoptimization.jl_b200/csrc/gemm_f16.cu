@@ -823,6 +823,232 @@ weight_prep16_kernel(const float* __restrict__ W, __half* __restrict__ W_hi, __h
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Fused optimiser step + operand refresh: ONE launch does what adam_kernel, adam_tick_kernel, wstats_kernel, plan_w_kernel,
+// L-1 weight_prep16_kernel launches and step_advance_kernel did one after the other (8 launches of 2-11 us each: at the
+// reference's small minibatches, and at the 8 192-row minibatches of the 8-GPU runs, such fixed costs are what is left).
+// All CTAs are co-resident (grid <= number of SMs) and meet at two grid-wide barriers:
+//   phase A  Adam (Flux.update!, src/train.jl:81; the maths of adam.cu, element for element) -- or, with data parallelism
+//            over peer memory, the rank-ordered sum of the published gradients first (dp_p2p.cu);
+//   phase B  weight statistics of the UPDATED parameters (exactly wstats_kernel's sums, same order of additions);
+//   phase C  scales (plan_w), fp16 hi/lo copies of W and W^T (weight_prep16), beta powers / exchange epoch / minibatch counter.
+// ---------------------------------------------------------------------------------------------
+struct F16RefreshArgs {
+    F16LayerTable t;
+    __half* W_hi[F_MAX_LAYERS]; __half* W_lo[F_MAX_LAYERS]; __half* WT_hi[F_MAX_LAYERS]; __half* WT_lo[F_MAX_LAYERS];
+    float* params;
+    unsigned* wstats;        // [4 L]
+    float* sc;
+    unsigned* bar;           // [2] grid-barrier counters (zero between launches)
+    // Adam (m == nullptr: refresh only)
+    float* m; float* v; const float* grads; long long P;
+    double eta, b1, b2, eps; double* bp;
+    // peer-memory gradient exchange (peer_xchg == nullptr: local gradient)
+    const float* const* peer_xchg; long long Ppad; const unsigned* flags; unsigned* p2p_state; int nranks; float* grads_out;
+    int* d_step;             // minibatch counter to advance (or nullptr)
+};
+
+__device__ __forceinline__ unsigned ld_acquire_gpu_u32(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned ld_acquire_sys_u32(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+// all CTAs of the (co-resident) grid arrive; the counter is reset by block 0 once the NEXT barrier has been passed
+__device__ __forceinline__ void grid_barrier(unsigned* ctr) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(ctr, 1u);
+        while (ld_acquire_gpu_u32(ctr) < gridDim.x) __nanosleep(32);
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(256)
+f16_adam_refresh_kernel(const F16RefreshArgs a) {
+    __shared__ float part[8][33];
+    __shared__ float tile[32][33];
+    __shared__ int s_abort;
+    const int L = a.t.L;
+    if (blockIdx.x == 0 && threadIdx.x == 0) a.bar[1] = 0u;      // (the previous launch is over; nobody is at barrier 2 yet)
+    // ---------------- phase A: Adam ----------------
+    if (a.m != nullptr) {
+        if (threadIdx.x == 0) s_abort = 0;
+        unsigned epoch = 0u;
+        if (a.peer_xchg != nullptr) {
+            epoch = a.p2p_state[0];
+            // a peer that never publishes must not hang the GPU: see p2p_adam_kernel (dp_p2p.cu)
+            if (threadIdx.x == 0) {
+                int abort_ = __ldcg(a.p2p_state + 2) != 0u;
+                const long long t0 = clock64();
+                unsigned long long g0 = 0ull;
+                if (blockIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g0));
+                for (int q = 0; q < a.nranks && !abort_; ++q)
+                    while (ld_acquire_sys_u32(a.flags + q) < epoch + 1u) {
+                        if (clock64() - t0 > 8000000000ll) { a.p2p_state[2] = 1u; abort_ = 1; break; }
+                        __nanosleep(64);
+                    }
+                if (blockIdx.x == 0) {      // diagnostic: time this rank spent waiting for its peers' gradients (ppo_policy_p2p_wait)
+                    unsigned long long g1;
+                    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g1));
+                    unsigned long long* acc = reinterpret_cast<unsigned long long*>(a.p2p_state + 4);
+                    acc[0] += g1 - g0;
+                    acc[1] += 1ull;
+                }
+                s_abort = abort_;
+            }
+        }
+        __syncthreads();
+        if (!s_abort) {
+            const size_t off = (size_t)(epoch & 1u) * (size_t)a.Ppad;
+            const double b1 = a.b1, b2 = a.b2;
+            const double b1p = a.bp[0], b2p = a.bp[1];
+            const double om1 = 1.0 - b1, om2 = 1.0 - b2;
+            const double c1 = 1.0 - b1p, c2 = 1.0 - b2p;
+            auto adam1 = [&](long long i, float g) {
+                const double gi = (double)g;
+                const float mt = (float)__dadd_rn(__dmul_rn(b1, (double)a.m[i]), __dmul_rn(om1, gi));
+                const float vt = (float)__dadd_rn(__dmul_rn(b2, (double)a.v[i]), __dmul_rn(__dmul_rn(om2, gi), gi));
+                a.m[i] = mt;
+                a.v[i] = vt;
+                const double den = __dadd_rn(sqrt((double)vt / c2), a.eps);
+                const float d = (float)__dmul_rn(((double)mt / c1) / den, a.eta);
+                a.params[i] = __fsub_rn(a.params[i], d);
+            };
+            if (a.peer_xchg != nullptr) {
+                // four parameters per thread and round: all 16-byte loads of the G peers' copies are in flight together
+                // (NVLink latency is paid once per round, not once per element); the sum runs in rank order on every
+                // rank, so the weights stay bit-identical across ranks
+                const long long n4 = a.P >> 2;
+                for (long long i4 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i4 < n4; i4 += (long long)gridDim.x * blockDim.x) {
+                    float4 acc = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                    float4 pv[8];
+                    for (int q0 = 0; q0 < a.nranks; q0 += 8) {
+#pragma unroll
+                        for (int u = 0; u < 8; ++u)
+                            if (q0 + u < a.nranks) pv[u] = __ldcv(reinterpret_cast<const float4*>(a.peer_xchg[q0 + u] + off) + i4);
+#pragma unroll
+                        for (int u = 0; u < 8; ++u)
+                            if (q0 + u < a.nranks) { acc.x += pv[u].x; acc.y += pv[u].y; acc.z += pv[u].z; acc.w += pv[u].w; }
+                    }
+                    if (a.grads_out != nullptr) reinterpret_cast<float4*>(a.grads_out)[i4] = acc;
+                    adam1(4 * i4, acc.x); adam1(4 * i4 + 1, acc.y); adam1(4 * i4 + 2, acc.z); adam1(4 * i4 + 3, acc.w);
+                }
+                if (blockIdx.x == 0 && (long long)threadIdx.x < (a.P & 3)) {
+                    const long long i = (n4 << 2) + threadIdx.x;
+                    float g = 0.0f;
+                    for (int q = 0; q < a.nranks; ++q) g += __ldcv(a.peer_xchg[q] + off + i);
+                    if (a.grads_out != nullptr) a.grads_out[i] = g;
+                    adam1(i, g);
+                }
+            } else {
+                for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.P; i += (long long)gridDim.x * blockDim.x)
+                    adam1(i, a.grads[i]);
+            }
+        }
+    }
+    if (blockIdx.x == 0) for (int i = threadIdx.x; i < 4 * L; i += blockDim.x) a.wstats[i] = 0u;
+    grid_barrier(a.bar + 0);
+    // ---------------- phase B: weight statistics (wstats_kernel's work items, spread over the grid) ----------------
+    {
+        const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
+        int base = 0;
+        for (int l = 0; l < L; ++l) {
+            const int K = a.t.K[l], N = a.t.N[l];
+            const int nbc = (N + 31) / 32, nbr = (K + 7) / 8;
+            const float* W = a.params + a.t.w_off[l];
+            const float* b = a.params + a.t.b_off[l];
+            // items [base, base + nbc + nbr) belong to layer l; item j is handled by block (j % gridDim.x)
+            int first = (int)blockIdx.x - base % (int)gridDim.x;
+            if (first < 0) first += (int)gridDim.x;
+            for (int it = first; it < nbc + nbr; it += (int)gridDim.x) {
+                float amax = 0.0f, colmax = 0.0f, rowmax = 0.0f, bmax = 0.0f;
+                if (it < nbc) {
+                    const int n = it * 32 + lane;
+                    float s = 0.0f;
+                    if (n < N)
+                        for (int k = grp; k < K; k += 8) { const float x = fabsf(W[(size_t)k * N + n]); s += x; amax = fmaxf(amax, x); }
+                    part[grp][lane] = s;
+                    __syncthreads();
+                    if (grp == 0 && n < N) {
+                        float c = 0.0f;
+#pragma unroll
+                        for (int g = 0; g < 8; ++g) c += part[g][lane];
+                        colmax = c;
+                        bmax = fabsf(b[n]);
+                    }
+                } else {
+                    const int k = (it - nbc) * 8 + grp;
+                    float s = 0.0f;
+                    if (k < K)
+                        for (int n = lane; n < N; n += 32) s += fabsf(W[(size_t)k * N + n]);
+#pragma unroll
+                    for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+                    rowmax = s;
+                }
+                amax = block_max_256(amax); colmax = block_max_256(colmax); rowmax = block_max_256(rowmax); bmax = block_max_256(bmax);
+                if (threadIdx.x == 0) {
+                    unsigned* st = a.wstats + 4 * l;
+                    if (amax > 0.0f) atomicMax(st + 0, __float_as_uint(amax));
+                    if (colmax > 0.0f) atomicMax(st + 1, __float_as_uint(colmax));
+                    if (rowmax > 0.0f) atomicMax(st + 2, __float_as_uint(rowmax));
+                    if (bmax > 0.0f) atomicMax(st + 3, __float_as_uint(bmax));
+                }
+            }
+            base += nbc + nbr;
+        }
+    }
+    grid_barrier(a.bar + 1);
+    // ---------------- phase C: scales, operand copies, counters ----------------
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        a.bar[0] = 0u;                       // every block has left barrier 1
+        for (int l = 0; l + 1 < L; ++l) write_scale(a.sc + 2 * sc_w(L, l), __uint_as_float(__ldcg(a.wstats + 4 * l)));
+        if (a.m != nullptr && !s_abort) { a.bp[0] *= a.b1; a.bp[1] *= a.b2; }
+        if (a.peer_xchg != nullptr) a.p2p_state[0] += 1u;
+        if (a.d_step != nullptr) *a.d_step += 1;
+    }
+    {
+        const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+        int base = 0;
+        for (int l = 0; l + 1 < L; ++l) {
+            const int K = a.t.K[l], N = a.t.N[l];
+            const int tn = (N + 31) / 32, tk = (K + 31) / 32;
+            const float* W = a.params + a.t.w_off[l];
+            float sc2[2];
+            write_scale(sc2, __uint_as_float(__ldcg(a.wstats + 4 * l)));      // (every block derives the same scale)
+            const float s = sc2[0];
+            int first = (int)blockIdx.x - base % (int)gridDim.x;
+            if (first < 0) first += (int)gridDim.x;
+            for (int it = first; it < tn * tk; it += (int)gridDim.x) {
+                const int k0 = (it / tn) * 32, n0 = (it % tn) * 32;
+                __syncthreads();
+                for (int r = ty; r < 32; r += 8) {
+                    const int k = k0 + r, n = n0 + tx;
+                    const float v = (k < K && n < N) ? W[(size_t)k * N + n] * s : 0.0f;
+                    tile[r][tx] = v;
+                    if (k < K && n < N) { __half h, lo; f16_split(v, h, lo); a.W_hi[l][(size_t)k * N + n] = h; a.W_lo[l][(size_t)k * N + n] = lo; }
+                }
+                __syncthreads();
+                for (int r = ty; r < 32; r += 8) {
+                    const int n = n0 + r, k = k0 + tx;
+                    if (n < N && k < K) {
+                        __half h, lo; f16_split(tile[tx][r], h, lo);
+                        a.WT_hi[l][(size_t)n * K + k] = h;
+                        a.WT_lo[l][(size_t)n * K + k] = lo;
+                    }
+                }
+            }
+            base += tn * tk;
+        }
+    }
+}
+
 // out[i] = (sum_z partial[z*stride + i]) * inv(sa) * inv(sb); fixed order: four interleaved chains over z (independent
 // loads in flight), folded as (s0 + s1) + (s2 + s3)
 __global__ void __launch_bounds__(256)
@@ -881,6 +1107,95 @@ f16_colsum_fold_kernel(const float* __restrict__ part, int64_t rows, int N, int6
     }
     for (; r < r1; ++r) s0 += part[r * N + n];
     out[(size_t)blockIdx.y * N + n] = (s0 + s1) + (s2 + s3);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Deferred reductions of the backward pass.  Every wgrad leaves split-K partials, every dgrad per-quarter column sums
+// (the bias gradient of the layer below), the head per-CTA partials; folding each right after its producer cost 9 small
+// launches per minibatch (f16_reduce x3, colsum_fold + reduce x2, colsum_fold + head_finish).  With separate partial
+// regions all of them are folded by TWO launches at the end of the backward pass, in exactly the same order of additions:
+//   stage 1: every job's rows are cut into `chunks` row ranges, each folded with four interleaved chains; a job with one
+//            chunk (split-K partials) is finished here (x the operands' inverse scales);
+//   stage 2: the chunk sums are folded (four chains; the head: two chains + scatter to dW / db / db_below).
+// ---------------------------------------------------------------------------------------------
+enum { FOLD_DIRECT = 0, FOLD_COLSUM = 1, FOLD_HEAD = 2 };
+struct FoldJob {
+    const float* src;        // [rows][N]
+    float* scratch;          // [chunks][N] (kinds 1, 2)
+    float* dst;              // kind 0: [N] (final); kind 1: [N]; kind 2: dW [K * Nh]
+    float* db; float* db_below;   // kind 2
+    const float* sa; const float* sb;   // kind 0: scale pairs of the two operands
+    int N, rows, chunks, kind;
+    int rows_from_tokens;    // kind 1: rows = 4 * ceil(active tokens / 128) when the pass was compacted
+    int K, Nh;               // kind 2
+    int begin1, begin2;      // first block of the job in stage 1 / stage 2
+};
+constexpr int FOLD_MAX_JOBS = 12;
+struct FoldJobs { int n; int blocks1, blocks2; const int* M_dev; FoldJob j[FOLD_MAX_JOBS]; };
+
+__global__ void __launch_bounds__(256)
+fold_stage1_kernel(const FoldJobs js) {
+    int ji = 0;
+    while (ji + 1 < js.n && (int)blockIdx.x >= js.j[ji + 1].begin1) ++ji;
+    const FoldJob& jb = js.j[ji];
+    const int local = (int)blockIdx.x - jb.begin1;
+    const int chunk = local % jb.chunks, cb = local / jb.chunks;
+    const int n = cb * 256 + threadIdx.x;
+    if (n >= jb.N) return;
+    int64_t rows = jb.rows;
+    if (jb.rows_from_tokens && js.M_dev != nullptr) {
+        const int64_t r = 4 * (((int64_t)__ldg(js.M_dev) + F_BM - 1) / F_BM);
+        rows = r < rows ? r : rows;
+    }
+    const int64_t rpc = (rows + jb.chunks - 1) / jb.chunks;
+    const int64_t r0 = (int64_t)chunk * rpc;
+    const int64_t r1 = r0 + rpc < rows ? r0 + rpc : rows;
+    const float* part = jb.src;
+    const int64_t N = jb.N;
+    float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
+    int64_t r = r0;
+    for (; r + 3 < r1; r += 4) {
+        s0 += part[r * N + n]; s1 += part[(r + 1) * N + n]; s2 += part[(r + 2) * N + n]; s3 += part[(r + 3) * N + n];
+    }
+    for (; r < r1; ++r) s0 += part[r * N + n];
+    const float s = (s0 + s1) + (s2 + s3);
+    if (jb.kind == FOLD_DIRECT) jb.dst[n] = s * (__ldg(jb.sa + 1) * __ldg(jb.sb + 1));
+    else jb.scratch[(size_t)chunk * N + n] = s;
+}
+
+__global__ void __launch_bounds__(256)
+fold_stage2_kernel(const FoldJobs js) {
+    int ji = -1;
+    for (int k = 0; k < js.n; ++k) {
+        const FoldJob& c = js.j[k];
+        if (c.kind != FOLD_DIRECT && (int)blockIdx.x >= c.begin2 && (int)blockIdx.x < c.begin2 + (c.N + 255) / 256) ji = k;
+    }
+    if (ji < 0) return;
+    const FoldJob& jb = js.j[ji];
+    const int i = ((int)blockIdx.x - jb.begin2) * 256 + threadIdx.x;
+    if (i >= jb.N) return;
+    const float* sc = jb.scratch;
+    const int64_t N = jb.N;
+    const int chunks = jb.chunks;
+    if (jb.kind == FOLD_COLSUM) {
+        float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
+        int z = 0;
+        for (; z + 3 < chunks; z += 4) {
+            s0 += sc[(size_t)z * N + i]; s1 += sc[(size_t)(z + 1) * N + i]; s2 += sc[(size_t)(z + 2) * N + i]; s3 += sc[(size_t)(z + 3) * N + i];
+        }
+        for (; z < chunks; ++z) s0 += sc[(size_t)z * N + i];
+        jb.dst[i] = (s0 + s1) + (s2 + s3);
+    } else {
+        float s0 = 0.0f, s1 = 0.0f;
+        int z = 0;
+        for (; z + 1 < chunks; z += 2) { s0 += sc[(size_t)z * N + i]; s1 += sc[(size_t)(z + 1) * N + i]; }
+        if (z < chunks) s0 += sc[(size_t)z * N + i];
+        const float s = s0 + s1;
+        const int KN = jb.K * jb.Nh;
+        if (i < KN) jb.dst[i] = s;
+        else if (i < KN + jb.Nh) jb.db[i - KN] = s;
+        else if (jb.db_below != nullptr) jb.db_below[i - KN - jb.Nh] = s;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1288,6 +1603,7 @@ struct F16State {
     int* tok_of_row = nullptr;               // [tokens] row -> token of the dense minibatch, ascending
     int* blk_counts = nullptr;               // [ceil(tokens / TOK_PER_BLOCK)] active tokens per block
     int* d_rows = nullptr;                   // number of active tokens of the current minibatch
+    unsigned* bar = nullptr;                 // grid-barrier counters of f16_adam_refresh_kernel
     bool compact = false;                    // the last forward pass ran compacted (the backward pass follows it)
 };
 
@@ -1307,12 +1623,15 @@ size_t head16_partial_bytes(int64_t M, int K, int N, int num_sms) {
     return (size_t)(head16_ctas(M, num_sms) + 64) * ((size_t)K * N + N + K) * sizeof(float);   // partials + fold scratch
 }
 
-size_t f16_partial_bytes(int64_t tokens, int K, int N, int num_sms) {
+size_t f16_wgrad_partial_bytes(int64_t tokens, int K, int N, int num_sms) {
     const int BN = N > 128 ? 256 : 128;
     const int tiles = (int)(ceil_div(K, F_BM) * ceil_div(N, BN));
-    const size_t a = (size_t)wgrad_splits16(tokens, tiles, num_sms) * K * N * 4;
-    const size_t c = ((size_t)4 * ceil_div(tokens, F_BM) + 64) * (size_t)std::max(K, N) * 4;   // dgrad-epilogue column sums
-    return std::max(a, c);
+    return (size_t)wgrad_splits16(tokens, tiles, num_sms) * K * N * 4;
+}
+// dgrad-epilogue column sums [4 * tiles_m][K] + the fold's scratch [64][K]
+size_t f16_colsum_partial_bytes(int64_t tokens, int K) { return ((size_t)4 * ceil_div(tokens, F_BM) + 64) * (size_t)K * 4; }
+size_t f16_partial_bytes(int64_t tokens, int K, int N, int num_sms) {
+    return std::max(f16_wgrad_partial_bytes(tokens, K, N, num_sms), f16_colsum_partial_bytes(tokens, std::max(K, N)));
 }
 
 int launch_absmax(ppo_ctx* ctx, const float* x, int64_t n, unsigned* out) {
@@ -1426,9 +1745,47 @@ int launch_mn16(ppo_ctx* ctx, const __half* X, const __half* X_lo, const __half*
     return PPO_OK;
 }
 
+// the deferred reductions of one backward pass: producers append jobs, fold_flush launches the two stages
+struct FoldList {
+    FoldJobs js{};
+    int add(const FoldJob& j) {
+        PPO_REQUIRE(js.n < FOLD_MAX_JOBS, "fold list full");
+        js.j[js.n++] = j;
+        return PPO_OK;
+    }
+};
+int fold_flush(ppo_ctx* ctx, FoldList& fl, const int* M_dev) {
+    FoldJobs& js = fl.js;
+    if (js.n == 0) return PPO_OK;
+    js.M_dev = M_dev;
+    int b1 = 0, b2 = 0;
+    for (int i = 0; i < js.n; ++i) {
+        FoldJob& j = js.j[i];
+        j.begin1 = b1; j.begin2 = b2;
+        b1 += (int)ceil_div(j.N, 256) * j.chunks;
+        if (j.kind != FOLD_DIRECT) b2 += (int)ceil_div(j.N, 256);
+    }
+    js.blocks1 = b1; js.blocks2 = b2;
+    fold_stage1_kernel<<<(unsigned)b1, 256, 0, ctx->stream>>>(js);
+    ctx->launches += 1;
+    if (b2 > 0) {
+        fold_stage2_kernel<<<(unsigned)b2, 256, 0, ctx->stream>>>(js);
+        ctx->launches += 1;
+    }
+    PPO_CUDA(cudaGetLastError());
+    return PPO_OK;
+}
+
 // fold [rows][N] per-quarter column sums (rows = 4 * tiles_m) into out[N]; scratch holds 64 * N floats
-int fold_colsum16(ppo_ctx* ctx, const float* part, int64_t rows, int N, float* scratch, float* out, const int* M_dev = nullptr) {
+int fold_colsum16(ppo_ctx* ctx, const float* part, int64_t rows, int N, float* scratch, float* out, const int* M_dev = nullptr,
+                  FoldList* defer = nullptr) {
     const int chunks = (int)std::min<int64_t>(64, rows);
+    if (defer != nullptr) {
+        FoldJob j{};
+        j.src = part; j.scratch = scratch; j.dst = out; j.N = N; j.rows = (int)rows; j.chunks = chunks; j.kind = FOLD_COLSUM;
+        j.rows_from_tokens = 1;
+        return defer->add(j);
+    }
     const int64_t rpc = ceil_div(rows, chunks);
     dim3 grid((unsigned)ceil_div(N, 256), (unsigned)chunks);
     f16_colsum_fold_kernel<<<grid, 256, 0, ctx->stream>>>(part, rows, N, rpc, scratch, M_dev);
@@ -1440,7 +1797,7 @@ int fold_colsum16(ppo_ctx* ctx, const float* part, int64_t rows, int N, float* s
 
 int wgrad16(ppo_ctx* ctx, const __half* X, const __half* X_lo, const __half* dY, const __half* dY_lo, float* dW,
             float* partial, size_t partial_bytes, int64_t M, int K, int N, const float* sc_x, const float* sc_dy,
-            const int* M_dev = nullptr) {
+            const int* M_dev = nullptr, FoldList* defer = nullptr) {
     PPO_REQUIRE(K % 8 == 0 && N % 32 == 0, "f16 wgrad: K %% 8 and N %% 32 required (K=%d N=%d)", K, N);
     const int BN = N > 128 ? 256 : 128;
     const int tiles = (int)(ceil_div(K, F_BM) * ceil_div(N, BN));
@@ -1449,6 +1806,11 @@ int wgrad16(ppo_ctx* ctx, const __half* X, const __half* X_lo, const __half* dY,
     if (BN == 256) PPO_TRY(launch_mn16<256>(ctx, X, X_lo, dY, dY_lo, M, K, N, partial, splits, M_dev));
     else PPO_TRY(launch_mn16<128>(ctx, X, X_lo, dY, dY_lo, M, K, N, partial, splits, M_dev));
     const int64_t cnt = (int64_t)K * N;
+    if (defer != nullptr) {
+        FoldJob j{};
+        j.src = partial; j.dst = dW; j.sa = sc_x; j.sb = sc_dy; j.N = (int)cnt; j.rows = splits; j.chunks = 1; j.kind = FOLD_DIRECT;
+        return defer->add(j);
+    }
     f16_reduce_kernel<<<(unsigned)ceil_div(cnt, 256), 256, 0, ctx->stream>>>(partial, splits, cnt, cnt, dW, sc_x, sc_dy);
     ctx->launches += 1;
     PPO_CUDA(cudaGetLastError());
@@ -1476,7 +1838,7 @@ int head_fwd16(ppo_ctx* ctx, const __half* H_hi, const __half* H_lo, const float
 int head_bwd16(ppo_ctx* ctx, const __half* H_hi, const __half* H_lo, const float* dlogits, const float* W, __half* dH_hi,
                __half* dH_lo, float* dW, float* db, float* db_below, int64_t M, int K, int N, float slope, float* partial,
                size_t partial_bytes, const float* sc_h, const float* sc_dh, const int* M_dev = nullptr,
-               const int* tok_of_row = nullptr) {
+               const int* tok_of_row = nullptr, FoldList* defer = nullptr) {
     PPO_REQUIRE(N >= 1 && N <= 4 && K % 4 == 0 && K >= 4 && K <= 1024, "f16 head_bwd: needs N <= 4, K %% 4 == 0, K <= 1024 (K=%d N=%d)", K, N);
     const int64_t ctas = head16_ctas(M, ctx->num_sms);
     const int64_t rows = ceil_div(M, ctas);
@@ -1498,6 +1860,12 @@ int head_bwd16(ppo_ctx* ctx, const __half* H_hi, const __half* H_lo, const float
     const int chunks = (int)std::min<int64_t>(64, ctas);
     const int64_t rpc = ceil_div(ctas, chunks);
     float* scratch = partial + (size_t)ctas * stride;
+    if (defer != nullptr) {
+        FoldJob j{};
+        j.src = partial; j.scratch = scratch; j.dst = dW; j.db = db; j.db_below = (db_below != nullptr && need_dH) ? db_below : nullptr;
+        j.N = (int)stride; j.rows = (int)ctas; j.chunks = chunks; j.kind = FOLD_HEAD; j.K = K; j.Nh = N;
+        return defer->add(j);
+    }
     f16_colsum_fold_kernel<<<dim3((unsigned)ceil_div(stride, 256), (unsigned)chunks), 256, 0, ctx->stream>>>(partial, ctas, (int)stride,
                                                                                                         rpc, scratch);
     head_finish_kernel<<<(unsigned)ceil_div(stride, 256), 256, 0, ctx->stream>>>(scratch, chunks, K, N, dW, db,
@@ -1546,9 +1914,12 @@ int ensure_f16_workspace(ppo_policy* p, int64_t tokens) {
     PPO_CUDA(cudaMalloc((void**)&st->tok_of_row, (size_t)tokens * sizeof(int)));
     PPO_CUDA(cudaMalloc((void**)&st->blk_counts, (size_t)ceil_div(tokens, TOK_PER_BLOCK) * sizeof(int)));
     if (st->d_rows == nullptr) PPO_CUDA(cudaMalloc((void**)&st->d_rows, sizeof(int)));
-    size_t pb = 16;
-    for (int l = 0; l + 1 < L; ++l) pb = std::max(pb, f16_partial_bytes(tokens, p->dims[l], p->dims[l + 1], ctx->num_sms));
-    pb = std::max(pb, head16_partial_bytes(tokens, p->dims[L - 1], p->dims[L], ctx->num_sms));
+    // one region per producer of the backward pass (head, every wgrad, every dgrad's column sums): their reductions are
+    // deferred to the end of the pass (fold_flush), so no two of them may share memory
+    size_t pb = 256;
+    for (int l = 0; l + 1 < L; ++l) pb += round_up(f16_wgrad_partial_bytes(tokens, p->dims[l], p->dims[l + 1], ctx->num_sms), 256);
+    for (int l = 1; l + 1 < L; ++l) pb += round_up(f16_colsum_partial_bytes(tokens, p->dims[l]), 256);
+    pb += round_up(head16_partial_bytes(tokens, p->dims[L - 1], p->dims[L], ctx->num_sms), 256);
     PPO_CUDA(cudaMalloc((void**)&st->partial, pb));
     st->partial_bytes = pb;
     st->tokens = tokens;
@@ -1597,33 +1968,52 @@ int f16_prepare(ppo_policy* p) {
         PPO_CUDA(cudaMalloc((void**)&st->st, nst * 4));
         PPO_CUDA(cudaMemsetAsync(st->sc, 0, nsc * 4, p->ctx->stream));
         PPO_CUDA(cudaMemsetAsync(st->st, 0, nst * 4, p->ctx->stream));
+        PPO_CUDA(cudaMalloc((void**)&st->bar, 64));
+        PPO_CUDA(cudaMemsetAsync(st->bar, 0, 64, p->ctx->stream));
     }
     return PPO_OK;
 }
 
-int f16_refresh_weights(ppo_policy* p) {
+// optimiser step (opt != nullptr) + weight statistics + scales + fp16 operand copies in ONE launch (see
+// f16_adam_refresh_kernel).  xv != nullptr: the gradient is the rank-ordered sum of the peers' published copies.
+// d_step: minibatch counter to advance at the end (CUDA-graph replay of the epoch loop), or nullptr.
+int f16_adam_refresh(ppo_policy* p, ppo_opt* opt, const P2PView* xv, int* d_step) {
     F16State* st = state(p);
     PPO_REQUIRE(st != nullptr, "fp16-split engine not prepared");
     ppo_ctx* ctx = p->ctx;
     const int L = p->L;
-    unsigned* wst = st->st + 2;
-    PPO_CUDA(cudaMemsetAsync(wst, 0, (size_t)4 * L * 4, ctx->stream));
-    int maxb = 1;
-    for (int l = 0; l < L; ++l) maxb = std::max(maxb, (int)(ceil_div(p->dims[l], 8) + ceil_div(p->dims[l + 1], 32)));
-    wstats_kernel<<<dim3((unsigned)maxb, (unsigned)L), 256, 0, ctx->stream>>>(p->params, st->table, wst);
-    plan_w_kernel<<<1, 32, 0, ctx->stream>>>(L, wst, st->sc);
-    ctx->launches += 2;
+    F16RefreshArgs a{};
+    a.t = st->table;
     for (int l = 0; l + 1 < L; ++l) {
-        const int K = p->dims[l], N = p->dims[l + 1];
-        F16Layer& ly = st->layers[l];
-        dim3 grid((unsigned)ceil_div(N, 32), (unsigned)ceil_div(K, 32));
-        weight_prep16_kernel<<<grid, 256, 0, ctx->stream>>>(p->params + p->w_off[l], ly.W_hi, ly.W_lo, ly.WT_hi, ly.WT_lo, K, N,
-                                                            st->sc + 2 * sc_w(L, l));
-        ctx->launches += 1;
+        a.W_hi[l] = st->layers[l].W_hi; a.W_lo[l] = st->layers[l].W_lo;
+        a.WT_hi[l] = st->layers[l].WT_hi; a.WT_lo[l] = st->layers[l].WT_lo;
     }
+    a.params = p->params; a.wstats = st->st + 2; a.sc = st->sc; a.bar = st->bar;
+    if (opt != nullptr) {
+        a.m = opt->m; a.v = opt->v; a.grads = p->grads; a.P = p->P;
+        a.eta = opt->eta; a.b1 = opt->beta1; a.b2 = opt->beta2; a.eps = opt->eps; a.bp = opt->d_bp;
+    }
+    if (xv != nullptr) {
+        PPO_REQUIRE(opt != nullptr, "fused refresh: the peer-memory exchange needs the optimiser");
+        a.peer_xchg = xv->peer_xchg; a.Ppad = xv->Ppad; a.flags = xv->flags; a.p2p_state = xv->state; a.nranks = xv->nranks;
+        a.grads_out = p->grads;
+    }
+    a.d_step = d_step;
+    // every CTA must be resident at once (grid-wide barriers): a few per SM (the Adam phase is latency-bound Float64
+    // maths, more resident warps hide it), never more than the occupancy calculator grants
+    static int per_sm = 0;
+    if (per_sm == 0) {
+        int occ = 0;
+        PPO_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, f16_adam_refresh_kernel, 256, 0));
+        per_sm = std::max(1, std::min(4, occ));
+    }
+    f16_adam_refresh_kernel<<<(unsigned)(ctx->num_sms * per_sm), 256, 0, ctx->stream>>>(a);
+    ctx->launches += 1;
     PPO_CUDA(cudaGetLastError());
     return PPO_OK;
 }
+
+int f16_refresh_weights(ppo_policy* p) { return f16_adam_refresh(p, nullptr, nullptr, nullptr); }
 
 int f16_forward(ppo_policy* p, const float* X, int64_t M, const float* mask) {
     F16State* st = state(p);
@@ -1680,36 +2070,58 @@ int f16_backward(ppo_policy* p, int64_t M) {
     plan_bwd_kernel<<<1, 32, 0, ctx->stream>>>(L, p->slope, st->st + 1, st->st + 2, st->sc);
     ctx->launches += 1;
     int pp = 0;
+    // The reductions of the partials (split-K, column sums, head) are deferred to two launches at the end of the pass --
+    // except under the per-layer overlapped NCCL all-reduce, which wants every layer's gradient as early as possible.
+    const bool per_layer = dp_overlap(ctx);
+    FoldList fl;
+    FoldList* defer = per_layer ? nullptr : &fl;
+    char* arena = reinterpret_cast<char*>(st->partial);
+    size_t arena_off = 0;
+    auto region = [&](size_t bytes) -> float* {
+        float* r = reinterpret_cast<float*>(arena + arena_off);
+        if (defer != nullptr) arena_off += round_up(bytes, 256);      // (eager reductions reuse the same memory)
+        return r;
+    };
     // head: dZ_{L-2}, dW_head, db_head and db_{L-2} = colsum(dZ_{L-2})
-    PPO_TRY(head_bwd16(ctx, st->act_hi[L - 1], st->act_lo[L - 1], p->dlogits, p->params + p->w_off[L - 1], st->dz_hi[pp],
-                       st->dz_lo[pp], p->grads + p->w_off[L - 1], p->grads + p->b_off[L - 1], p->grads + p->b_off[L - 2], M,
-                       p->dims[L - 1], p->dims[L], p->slope, st->partial, st->partial_bytes, st->sc + 2 * sc_act(L - 1),
-                       st->sc + 2 * sc_dz(L, L - 2), M_dev, tok));
+    {
+        const size_t hb = head16_partial_bytes(M, p->dims[L - 1], p->dims[L], ctx->num_sms);
+        float* part = region(hb);
+        PPO_TRY(head_bwd16(ctx, st->act_hi[L - 1], st->act_lo[L - 1], p->dlogits, p->params + p->w_off[L - 1], st->dz_hi[pp],
+                           st->dz_lo[pp], p->grads + p->w_off[L - 1], p->grads + p->b_off[L - 1], p->grads + p->b_off[L - 2], M,
+                           p->dims[L - 1], p->dims[L], p->slope, part, st->partial_bytes - (size_t)((char*)part - arena),
+                           st->sc + 2 * sc_act(L - 1), st->sc + 2 * sc_dz(L, L - 2), M_dev, tok, defer));
+    }
     // data parallelism: a layer's slice of the flat gradient vector (dW_l, db_l: contiguous in Flux.params order) is
     // all-reduced on the communication stream as soon as it is complete, while the layers below still compute
-    PPO_TRY(grads_ready(ctx, p->grads + p->w_off[L - 1], p->P - p->w_off[L - 1]));
+    if (per_layer) PPO_TRY(grads_ready(ctx, p->grads + p->w_off[L - 1], p->P - p->w_off[L - 1]));
     for (int l = L - 2; l >= 0; --l) {
         const int K = p->dims[l], N = p->dims[l + 1];
         F16Layer& ly = st->layers[l];
         const __half* X_hi = (l == 0) ? st->x_hi : st->act_hi[l];
         const __half* X_lo = (l == 0) ? st->x_lo : st->act_lo[l];
         const float* sc_dy = st->sc + 2 * sc_dz(L, l);
-        PPO_TRY(wgrad16(ctx, X_hi, X_lo, st->dz_hi[pp], st->dz_lo[pp], p->grads + p->w_off[l], st->partial, st->partial_bytes, M,
-                        K, N, st->sc + 2 * sc_act(l), sc_dy, M_dev));
-        PPO_TRY(grads_ready(ctx, p->grads + p->w_off[l], p->w_off[l + 1] - p->w_off[l]));      // dW_l and db_l (db_l came from above)
+        {
+            float* part = region(f16_wgrad_partial_bytes(M, K, N, ctx->num_sms));
+            PPO_TRY(wgrad16(ctx, X_hi, X_lo, st->dz_hi[pp], st->dz_lo[pp], p->grads + p->w_off[l], part,
+                            st->partial_bytes - (size_t)((char*)part - arena), M, K, N, st->sc + 2 * sc_act(l), sc_dy, M_dev, defer));
+        }
+        if (per_layer) PPO_TRY(grads_ready(ctx, p->grads + p->w_off[l], p->w_off[l + 1] - p->w_off[l]));      // dW_l and db_l (db_l came from above)
         if (l > 0) {
+            float* part = region(f16_colsum_partial_bytes(M, K));
             KK16Params kp{};
             kp.epi = F_EPI_DGRAD; kp.act = 0; kp.slope = p->slope; kp.gate = st->act_sign[l];
-            kp.colsum_partial = st->partial;
+            kp.colsum_partial = part;
             kp.M_dev = M_dev;
             kp.sc_a = sc_dy; kp.sc_b = st->sc + 2 * sc_w(L, l); kp.sc_c = st->sc + 2 * sc_dz(L, l - 1);
             // dX[M, K] = dY[M, N] * W[K, N]^T : A = dY (K-major in N), B = W rows (K-major in N)
             PPO_TRY(kk16_dispatch(ctx, st->dz_hi[pp], st->dz_lo[pp], ly.W_hi, ly.W_lo, st->dz_hi[pp ^ 1], st->dz_lo[pp ^ 1], M, K, N, kp));
             const int64_t rows = 4 * ceil_div(M, F_BM);
-            PPO_TRY(fold_colsum16(ctx, st->partial, rows, K, st->partial + (size_t)rows * K, p->grads + p->b_off[l - 1], M_dev));
+            PPO_TRY(fold_colsum16(ctx, part, rows, K, part + (size_t)rows * K, p->grads + p->b_off[l - 1], M_dev, defer));
             pp ^= 1;
         }
     }
+    PPO_REQUIRE(arena_off <= st->partial_bytes, "fp16-split engine: partial arena too small");
+    if (defer != nullptr) PPO_TRY(fold_flush(ctx, fl, M_dev));
     return PPO_OK;
 }
 
@@ -1757,7 +2169,7 @@ void f16_destroy(ppo_policy* p) {
     for (auto& a : st->act_hi) fr(a);
     for (auto& a : st->act_lo) fr(a);
     for (auto& a : st->act_sign) fr(a);
-    fr(st->sc); fr(st->st); fr(st->tok_of_row); fr(st->blk_counts); fr(st->d_rows);
+    fr(st->sc); fr(st->st); fr(st->tok_of_row); fr(st->blk_counts); fr(st->d_rows); fr(st->bar);
     delete st;
     p->f16 = nullptr;
 }

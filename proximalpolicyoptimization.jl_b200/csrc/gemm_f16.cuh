@@ -10,6 +10,9 @@ namespace ppo {
 int f16_prepare(ppo_policy* p);
 // weight statistics (abs-max, max column / row abs-sums) -> scales -> fp16 hi/lo copies of W and W^T
 int f16_refresh_weights(ppo_policy* p);
+// the same preceded by the Adam step, all in one launch; xv: peer-memory gradient exchange (dp_p2p.cu) or nullptr;
+// d_step: device minibatch counter to advance, or nullptr
+int f16_adam_refresh(ppo_policy* p, ppo_opt* opt, const P2PView* xv, int* d_step);
 // whole-MLP forward: X fp32 [M][dims[0]] -> p->act[L] (fp32 logits); hidden activations stay fp16 hi/lo pairs.
 // mask (optional): the minibatch's action mask [M * apa]; with p->compact_tokens the MLP then runs only on the tokens
 // that have at least one unmasked action (the logits of the others never reach the loss: softmax(-Inf) = 0)

@@ -114,6 +114,12 @@ class Policy:
         assert len(handles) == 64 * nranks
         _lib.check(_lib.load().ppo_policy_p2p_connect(self.handle, int(nranks), int(rank), C.c_char_p(handles)))
 
+    def p2p_wait(self, reset: bool = False):
+        """(total ns, waits): time this rank's optimiser kernel spent waiting for its peers' gradients"""
+        ns, n = C.c_int64(0), C.c_int64(0)
+        _lib.check(_lib.load().ppo_policy_p2p_wait(self.handle, C.byref(ns), C.byref(n), 1 if reset else 0))
+        return int(ns.value), int(n.value)
+
     @property
     def gemm_mode(self) -> int:
         return int(_lib.load().ppo_policy_get_gemm_mode(self.handle))
