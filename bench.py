@@ -394,6 +394,10 @@ def kernel_rooflines(h, cfg, B_local, gemm):
     k1 = hbm("K1_scan_64M", "scan", 64 * 1024 * 1024, 15, iters=5)
     k1g = hbm("K1_scan_64M_gamma0.99", "scan", 64 * 1024 * 1024, 15, 1, iters=5)
     k2 = hbm("K1K2_scan_64M_with_norm_stats", "scan_norm", 64 * 1024 * 1024, 15, iters=5)
+    # stress variants: episodes as long as a whole scan tile (4 096 transitions: the look-ahead window
+    # misses, every tile looks back one or two tiles), and ONE unterminated episode over all 64 M transitions (every
+    # tile's carry depends on every tile to its right: the decoupled look-back's worst case)
+    k1s = hbm("K1_scan_64M_episodes4096_gamma0.99", "scan", 64 * 1024 * 1024, 4096, 1, iters=3)
     k1l = hbm("K1_scan_64M_longepisodes_gamma0.99", "scan", 64 * 1024 * 1024, 1 << 30, 1, iters=3)
     hbm("K3_shuffle", "shuffle", cfg.N)
     k4 = hbm("K4_gather_ldg", "gather0", cfg.N, cfg.nf * cfg.nhe, cfg.A, B_local)
@@ -430,7 +434,8 @@ def kernel_rooflines(h, cfg, B_local, gemm):
                 "frac_of_3pass_ceiling": round(ach / ceiling, 4) if passes == 3 else None,
                 # the HBM-bound kernels of the path against the measured copy peak (>> L2 sizes; named sizes in `kernels`)
                 "hbm": {"peak_gbs": pk["hbm"], "K1_scan_64M": k1["frac"], "K1_scan_64M_gamma0.99": k1g["frac"],
-                        "K1K2_scan_with_norm_stats": k2["frac"], "K1_scan_64M_one_episode": k1l["frac"],
+                        "K1K2_scan_with_norm_stats": k2["frac"], "K1_scan_64M_episodes_of_4096": k1s["frac"],
+                        "K1_scan_64M_one_episode": k1l["frac"],
                         "K4_gather": k4["frac"], "K6_loss_1M": k6["frac"]},
                 "detail": dom}
     return roofline, kernels

@@ -1133,15 +1133,18 @@ struct FoldJob {
 constexpr int FOLD_MAX_JOBS = 12;
 struct FoldJobs { int n; int blocks1, blocks2; const int* M_dev; FoldJob j[FOLD_MAX_JOBS]; };
 
+// columns per stage-1 block: column sums have many rows and few columns (4 * tiles_m x K): 64-column blocks whose four
+// 64-thread groups take every fourth row keep hundreds of blocks busy with 64 chunks; the others use one column per thread
+__host__ __device__ inline int fold_block_cols(int kind) { return kind == FOLD_COLSUM ? 64 : 256; }
+
 __global__ void __launch_bounds__(256)
 fold_stage1_kernel(const FoldJobs js) {
+    __shared__ float sub[4][64];
     int ji = 0;
     while (ji + 1 < js.n && (int)blockIdx.x >= js.j[ji + 1].begin1) ++ji;
     const FoldJob& jb = js.j[ji];
     const int local = (int)blockIdx.x - jb.begin1;
     const int chunk = local % jb.chunks, cb = local / jb.chunks;
-    const int n = cb * 256 + threadIdx.x;
-    if (n >= jb.N) return;
     int64_t rows = jb.rows;
     if (jb.rows_from_tokens && js.M_dev != nullptr) {
         const int64_t r = 4 * (((int64_t)__ldg(js.M_dev) + F_BM - 1) / F_BM);
@@ -1152,6 +1155,22 @@ fold_stage1_kernel(const FoldJobs js) {
     const int64_t r1 = r0 + rpc < rows ? r0 + rpc : rows;
     const float* part = jb.src;
     const int64_t N = jb.N;
+    if (jb.kind == FOLD_COLSUM) {
+        const int c = threadIdx.x & 63, g = threadIdx.x >> 6;
+        const int n = cb * 64 + c;
+        float s0 = 0.0f, s1 = 0.0f;
+        if (n < jb.N) {
+            int64_t r = r0 + g;
+            for (; r + 4 < r1; r += 8) { s0 += part[r * N + n]; s1 += part[(r + 4) * N + n]; }
+            if (r < r1) s0 += part[r * N + n];
+        }
+        sub[g][c] = s0 + s1;
+        __syncthreads();
+        if (g == 0 && n < jb.N) jb.scratch[(size_t)chunk * N + n] = (sub[0][c] + sub[1][c]) + (sub[2][c] + sub[3][c]);
+        return;
+    }
+    const int n = cb * 256 + threadIdx.x;
+    if (n >= jb.N) return;
     float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
     int64_t r = r0;
     for (; r + 3 < r1; r += 4) {
@@ -1628,6 +1647,8 @@ size_t f16_wgrad_partial_bytes(int64_t tokens, int K, int N, int num_sms) {
     const int tiles = (int)(ceil_div(K, F_BM) * ceil_div(N, BN));
     return (size_t)wgrad_splits16(tokens, tiles, num_sms) * K * N * 4;
 }
+// row chunks of the column-sum fold (the second stage adds them serially: keep it short)
+inline int colsum_chunks(int64_t rows) { return (int)std::max<int64_t>(1, std::min<int64_t>(64, rows)); }
 // dgrad-epilogue column sums [4 * tiles_m][K] + the fold's scratch [64][K]
 size_t f16_colsum_partial_bytes(int64_t tokens, int K) { return ((size_t)4 * ceil_div(tokens, F_BM) + 64) * (size_t)K * 4; }
 size_t f16_partial_bytes(int64_t tokens, int K, int N, int num_sms) {
@@ -1762,7 +1783,7 @@ int fold_flush(ppo_ctx* ctx, FoldList& fl, const int* M_dev) {
     for (int i = 0; i < js.n; ++i) {
         FoldJob& j = js.j[i];
         j.begin1 = b1; j.begin2 = b2;
-        b1 += (int)ceil_div(j.N, 256) * j.chunks;
+        b1 += (int)ceil_div(j.N, fold_block_cols(j.kind)) * j.chunks;
         if (j.kind != FOLD_DIRECT) b2 += (int)ceil_div(j.N, 256);
     }
     js.blocks1 = b1; js.blocks2 = b2;
@@ -1779,7 +1800,7 @@ int fold_flush(ppo_ctx* ctx, FoldList& fl, const int* M_dev) {
 // fold [rows][N] per-quarter column sums (rows = 4 * tiles_m) into out[N]; scratch holds 64 * N floats
 int fold_colsum16(ppo_ctx* ctx, const float* part, int64_t rows, int N, float* scratch, float* out, const int* M_dev = nullptr,
                   FoldList* defer = nullptr) {
-    const int chunks = (int)std::min<int64_t>(64, rows);
+    const int chunks = colsum_chunks(rows);
     if (defer != nullptr) {
         FoldJob j{};
         j.src = part; j.scratch = scratch; j.dst = out; j.N = N; j.rows = (int)rows; j.chunks = chunks; j.kind = FOLD_COLSUM;
