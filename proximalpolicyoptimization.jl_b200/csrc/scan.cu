@@ -5,20 +5,20 @@
 //     v <- rewards[i] + discount * (terminal[i] ? 0 : v_next)        for i = n .. 1
 // Each transition is the affine map c -> b_i + a_i c with (a_i, b_i) = (terminal_i ? 0 : g, r_i);
 // the scan composes maps right to left.  One pass over HBM (read 4 B reward + 1 B terminal,
-// write 4 B return = 9 B/transition): single-pass chained scan with decoupled look-back.
-// Tile ids are blockIdx.x counted from the RIGHT end (the scan runs right to left), so a tile
-// only waits on lower-numbered blocks, which the hardware dispatches first (the forward-progress
-// assumption CUB's DeviceScan makes).  A global atomic ticket was measured to serialise at ~27
-// cycles per tile (0.23 of the 0.31 ms for 64 M transitions) and was removed.  The carry is Float64 exactly like Julia's promoted `v` (the reference
-// passes a Float64 discount everywhere); inside a thread's 16-item chunk the recurrence is the
+// write 4 B return = 9 B/transition): single-pass chained scan with decoupled look-back whose
+// tile is ONE WARP's 512 transitions; warps are persistent and never synchronise with each other
+// (see returns_scan_kernel).  Tile ids count from the RIGHT end (the scan runs right to left), so a
+// tile only waits on lower-numbered tiles, which co-resident warps with lower ids process first or
+// at the same time.  The carry is Float64 exactly like Julia's promoted `v` (the reference passes
+// a Float64 discount everywhere); inside a thread's 16-item chunk the recurrence is the
 // reference's serial loop with unfused multiply/add, so any chunk that starts right of an
 // episode end is bit-identical to the serial result, and with discount == 1 and integer
 // rewards every value is exact.
 //
 // The kernel runs out of place (the rollout buffer swaps its reward/return arrays afterwards, which is what
 // `rollouts.rewards .= compute_returns(...)` amounts to).
-// Memory layout: rewards float[n], terminal uint8[n]; thread t of a tile owns 16 consecutive
-// transitions = 4 x LDG.128 + 1 x LDG.128 in flight, 4 x STG.128 out.
+// Memory layout: rewards float[n], terminal uint8[n]; lane l of a warp owns 16 consecutive
+// transitions = 4 x cp.async 16 B + 1 x cp.async 16 B in flight one tile ahead, 4 x STG.128 out.
 #include <algorithm>
 
 #include "common.cuh"
@@ -106,35 +106,41 @@ __device__ __forceinline__ double warp_lookback(const ScanScratch sc, int t, int
     }
 }
 
-constexpr int SCAN_LOOK = 128;   // transitions right of the tile inspected for an episode end (4 per lane of warp 0)
+constexpr int SCAN_LOOK = 128;   // transitions right of a warp tile inspected for an episode end (4 per lane)
+constexpr int SCAN_WT = 32 * SCAN_ITEMS;       // transitions per warp tile (512)
+constexpr int SCAN_WARPS = SCAN_THREADS / 32;
 
-// one pipeline stage in shared memory: the tile's rewards in the padded blocked arrangement, its terminals, and
-// the look-ahead window
 // float offset of 16-byte piece j (0..3) of chunk c (0..31) inside a warp's region (chunks padded to 20 floats)
 __device__ __forceinline__ int sx_off(int c, int j) { return c * 20 + j * 4; }
 
-struct __align__(16) ScanStage {
-    float x[SCAN_THREADS / 32][32 * 20];     // per warp: 32 chunks of 16 items padded to 20 floats (conflict-free)
-    uint8_t t[SCAN_TILE];
-    float lx[SCAN_LOOK];
-    uint8_t lt[SCAN_LOOK];
+// one pipeline stage of ONE WARP in shared memory: its 512 rewards in the padded blocked arrangement and its terminals
+struct __align__(16) WarpStage {
+    float x[32 * 20];        // 32 chunks of 16 items padded to 20 floats (conflict-free 128-bit accesses)
+    uint8_t t[SCAN_WT];
 };
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc)
                  : "memory");
 }
-__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc)
-                 : "memory");
-}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-// Persistent CTAs: block b scans tiles b, b + G, b + 2G, ... (tile ids count from the RIGHT end, the direction of the
-// scan), G = all co-resident CTAs.  While tile i is being scanned, the cp.async copies of tile i+1 are in flight, so
-// HBM always has work queued; before this software pipeline the kernel was latency bound at ~55 % of the roofline.
+// Persistent WARPS: the scan tile is one warp's 512 transitions, and a warp never synchronises with the other warps of its
+// CTA (the earlier CTA-wide tile spent 28 % of its issue cycles at the per-tile __syncthreads: profiles/r02_scan_ncu.md).
+// Warp g scans warp tiles g, g + W, g + 2W, ... (ids count from the RIGHT end, the direction of the scan; W = all
+// co-resident warps).  While a tile is being scanned the cp.async copies of the warp's next tile are in flight.
+//
+// Where a tile's incoming carry comes from:
+//   * look-ahead: the 128 transitions right of the tile (prefetched into registers one tile ahead), composed into one
+//     affine map.  With episodic data an episode end almost always lies inside it, and the carry is known without
+//     waiting for anybody;
+//   * otherwise the decoupled look-back over the tiles to the right (aggregates / inclusive values in global memory).
+// A tile publishes its aggregate / inclusive value ONLY IF its own first 128 transitions hold no episode end: exactly
+// then its left neighbour's look-ahead misses and reads them.  (A tile whose look-ahead hit publishes its inclusive value
+// directly, which ends any look-back that reaches it, so nobody ever waits on a tile that does not publish.)
+//
 // G1: discount == 1 (every in-tree use of the reference): g * v == v exactly, so the multiplies are dropped
 // (bit-identical results, fewer Float64 instructions).
 template <bool F32CARRY, bool G1>
@@ -142,57 +148,48 @@ __global__ void __launch_bounds__(SCAN_THREADS, 4)
 returns_scan_kernel(const float* __restrict__ rew, float* __restrict__ out, const uint8_t* __restrict__ term, int64_t n,
                     double g, double g8, int tiles, ScanScratch sc, double* __restrict__ tile_stats) {
     extern __shared__ __align__(16) unsigned char scan_smem[];
-    ScanStage* stages = reinterpret_cast<ScanStage*>(scan_smem);
-    // block-shared scratch, double-buffered by iteration parity: with a single __syncthreads per tile a warp can
-    // run at most one barrier ahead of the slowest warp, so parity buffering rules out write-after-read races
-    __shared__ double sA2[2][SCAN_THREADS / 32], sB2[2][SCAN_THREADS / 32];
-    __shared__ double s_carry2[2];
-    __shared__ double s_lookA2[2], s_lookB2[2];
-
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    constexpr int NW = SCAN_THREADS / 32;
+    WarpStage* stages = reinterpret_cast<WarpStage*>(scan_smem) + 2 * warp;      // this warp's two stages
 
-    // issue the asynchronous copies of tile t into a stage (full tiles only; the single partial tile, t == 0 when
-    // n is not a multiple of the tile, is read directly below)
-    auto issue = [&](int t, ScanStage& st) {
-        const int tile_idx = tiles - 1 - t;
-        const int64_t tile_base = (int64_t)tile_idx * SCAN_TILE;
-        if (tile_base + SCAN_TILE <= n) {
-            const float* src = rew + tile_base + (int64_t)warp * (32 * SCAN_ITEMS);
+    // look-ahead window of a tile, one register set ahead of its use
+    float4 la_r = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    uint32_t la_t = 0u;
+    // asynchronous copies of warp tile t into a stage (full tiles only; a partial tile is read directly below) and the
+    // plain loads of its look-ahead window
+    auto issue = [&](int t, WarpStage& st, float4& lr, uint32_t& lt) {
+        const int64_t tile_base = (int64_t)(tiles - 1 - t) * SCAN_WT;
+        if (tile_base + SCAN_WT <= n) {
+            const float* src = rew + tile_base;
 #pragma unroll
             for (int q = 0; q < SCAN_ITEMS / 4; ++q)      // element e = 128 q + 4 lane of the warp's 512
-                cp_async16(&st.x[warp][sx_off(q * 8 + (lane >> 2), lane & 3)], src + q * 128 + 4 * lane);
-            cp_async16(&st.t[tid * SCAN_ITEMS], term + tile_base + (int64_t)tid * SCAN_ITEMS);
-            if (warp == 0) {
-                const int64_t e0 = tile_base + SCAN_TILE + 4 * lane;
-                if (e0 + 4 <= n) {
-                    cp_async16(&st.lx[4 * lane], rew + e0);
-                    cp_async4(&st.lt[4 * lane], term + e0);
-                }
+                cp_async16(&st.x[sx_off(q * 8 + (lane >> 2), lane & 3)], src + q * 128 + 4 * lane);
+            cp_async16(&st.t[lane * SCAN_ITEMS], term + tile_base + (int64_t)lane * SCAN_ITEMS);
+            const int64_t e0 = tile_base + SCAN_WT + 4 * lane;
+            if (e0 + 4 <= n) {
+                lr = __ldg(reinterpret_cast<const float4*>(rew + e0));
+                lt = __ldg(reinterpret_cast<const uint32_t*>(term + e0));
             }
         }
         cp_async_commit();
     };
 
-    int t = (int)blockIdx.x;
-    if (t < tiles) issue(t, stages[0]);
-    for (int it = 0; t < tiles; t += (int)gridDim.x, ++it) {
-        ScanStage& st = stages[it & 1];
-        double* sA = sA2[it & 1];
-        double* sB = sB2[it & 1];
-        double& s_lookA = s_lookA2[it & 1];
-        double& s_lookB = s_lookB2[it & 1];
-        double& s_carry = s_carry2[it & 1];
-        const int t_next = t + (int)gridDim.x;
-        if (t_next < tiles) { issue(t_next, stages[(it + 1) & 1]); cp_async_wait<1>(); }
+    const int wstride = (int)gridDim.x * SCAN_WARPS;
+    int t = (int)blockIdx.x * SCAN_WARPS + warp;
+    float4 nx_r = la_r; uint32_t nx_t = la_t;
+    if (t < tiles) issue(t, stages[0], nx_r, nx_t);
+    for (int it = 0; t < tiles; t += wstride, ++it) {
+        WarpStage& st = stages[it & 1];
+        la_r = nx_r; la_t = nx_t;
+        const int t_next = t + wstride;
+        if (t_next < tiles) { issue(t_next, stages[(it + 1) & 1], nx_r, nx_t); cp_async_wait<1>(); }
         else cp_async_wait<0>();
         __syncwarp();
 
         const int tile_idx = tiles - 1 - t;         // position from the left
-        const int64_t tile_base = (int64_t)tile_idx * SCAN_TILE;
-        const bool full_tile = tile_base + SCAN_TILE <= n;
-        const int64_t base = tile_base + (int64_t)tid * SCAN_ITEMS;
-        float* wx = st.x[warp];
+        const int64_t tile_base = (int64_t)tile_idx * SCAN_WT;
+        const bool full_tile = tile_base + SCAN_WT <= n;
+        const int64_t base = tile_base + (int64_t)lane * SCAN_ITEMS;
+        float* wx = st.x;
 
         float r[SCAN_ITEMS];
         uint32_t tm[SCAN_ITEMS / 4];
@@ -202,7 +199,7 @@ returns_scan_kernel(const float* __restrict__ rew, float* __restrict__ out, cons
                 const float4 v = *reinterpret_cast<const float4*>(wx + sx_off(lane, q));
                 r[4 * q + 0] = v.x; r[4 * q + 1] = v.y; r[4 * q + 2] = v.z; r[4 * q + 3] = v.w;
             }
-            const uint4 tv = *reinterpret_cast<const uint4*>(&st.t[tid * SCAN_ITEMS]);
+            const uint4 tv = *reinterpret_cast<const uint4*>(&st.t[lane * SCAN_ITEMS]);
             tm[0] = tv.x; tm[1] = tv.y; tm[2] = tv.z; tm[3] = tv.w;
         } else {
 #pragma unroll
@@ -225,19 +222,16 @@ returns_scan_kernel(const float* __restrict__ rew, float* __restrict__ out, cons
                                (((tm[2] * 0x01020408u) >> 24 & 0xfu) << 8) | (((tm[3] * 0x01020408u) >> 24 & 0xfu) << 12);
         auto is_term = [&](int i) -> bool { return (tbits >> i) & 1u; };
 
-        // 0. look-ahead (warp 0): the 128 transitions right of the tile, composed into one map.  With episodic
-        //    data an episode end almost always lies inside it (A == 0), so the tile's incoming carry is known
-        //    without waiting for any other CTA; only tiles inside very long episodes use the look-back below.
-        if (warp == 0) {
-            const int64_t e0 = tile_base + SCAN_TILE + 4 * lane;
+        // 0. look-ahead: the 128 transitions right of the tile, composed into one map (the same value in every lane)
+        double lookA, lookB;
+        {
+            const int64_t e0 = tile_base + SCAN_WT + 4 * lane;
             Map lk{1.0, 0.0};
             float lr[4]; bool lt[4];
             if (full_tile && e0 + 4 <= n) {
-                const float4 v = *reinterpret_cast<const float4*>(&st.lx[4 * lane]);
-                const uint32_t tb = *reinterpret_cast<const uint32_t*>(&st.lt[4 * lane]);
-                lr[0] = v.x; lr[1] = v.y; lr[2] = v.z; lr[3] = v.w;
+                lr[0] = la_r.x; lr[1] = la_r.y; lr[2] = la_r.z; lr[3] = la_r.w;
 #pragma unroll
-                for (int j = 0; j < 4; ++j) lt[j] = ((tb >> (8 * j)) & 0xffu) != 0;
+                for (int j = 0; j < 4; ++j) lt[j] = ((la_t >> (8 * j)) & 0xffu) != 0;
             } else {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
@@ -263,20 +257,22 @@ returns_scan_kernel(const float* __restrict__ rew, float* __restrict__ out, cons
                 lk.B = part;
             } else {
 #pragma unroll
-            for (int j = 3; j >= 0; --j) {
-                const double a = lt[j] ? 0.0 : g;
-                lk.B = __dadd_rn((double)lr[j], __dmul_rn(a, lk.B));
-                lk.A = a * lk.A;
-            }
+                for (int j = 3; j >= 0; --j) {
+                    const double a = lt[j] ? 0.0 : g;
+                    lk.B = __dadd_rn((double)lr[j], __dmul_rn(a, lk.B));
+                    lk.A = a * lk.A;
+                }
 #pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                Map o;
-                o.A = __shfl_down_sync(0xffffffffu, lk.A, d);
-                o.B = __shfl_down_sync(0xffffffffu, lk.B, d);
-                if (lane + d < 32) lk = compose(lk, o);
+                for (int d = 1; d < 32; d <<= 1) {
+                    Map o;
+                    o.A = __shfl_down_sync(0xffffffffu, lk.A, d);
+                    o.B = __shfl_down_sync(0xffffffffu, lk.B, d);
+                    if (lane + d < 32) lk = compose(lk, o);
+                }
+                lk.A = __shfl_sync(0xffffffffu, lk.A, 0);
+                lk.B = __shfl_sync(0xffffffffu, lk.B, 0);
             }
-            }
-            if (lane == 0) { s_lookA = lk.A; s_lookB = lk.B; }
+            lookA = lk.A; lookB = lk.B;
         }
 
         // 1. per-thread aggregate map, right to left (B is the serial recurrence with zero carry).  The 16 items
@@ -284,7 +280,6 @@ returns_scan_kernel(const float* __restrict__ rew, float* __restrict__ out, cons
         //    pairs), combined as left(right(c)).
         constexpr int HALF = SCAN_ITEMS / 2;
         double Bh = 0.0, Bl = 0.0;
-        bool th = false, tl = false;
 #pragma unroll
         for (int i = HALF - 1; i >= 0; --i) {
             const bool t_hi = is_term(i + HALF), t_lo = is_term(i);
@@ -296,7 +291,7 @@ returns_scan_kernel(const float* __restrict__ rew, float* __restrict__ out, cons
                 Bl = __dadd_rn((double)r[i], __dmul_rn(t_lo ? 0.0 : g, Bl));
             }
         }
-        th = (tbits >> HALF) != 0u; tl = (tbits & ((1u << HALF) - 1u)) != 0u;
+        const bool th = (tbits >> HALF) != 0u, tl = (tbits & ((1u << HALF) - 1u)) != 0u;
         const double Ah = th ? 0.0 : g8, Al = tl ? 0.0 : g8;
         Map me;
         me.A = Al * Ah;
@@ -315,54 +310,41 @@ returns_scan_kernel(const float* __restrict__ rew, float* __restrict__ out, cons
         lane_excl.A = __shfl_down_sync(0xffffffffu, inc.A, 1);
         lane_excl.B = __shfl_down_sync(0xffffffffu, inc.B, 1);
         if (lane == 31) { lane_excl.A = 1.0; lane_excl.B = 0.0; }
-        if (lane == 0) { sA[warp] = inc.A; sB[warp] = inc.B; }
-        __syncthreads();
+        Map tile;       // the whole warp tile
+        tile.A = __shfl_sync(0xffffffffu, inc.A, 0);
+        tile.B = __shfl_sync(0xffffffffu, inc.B, 0);
 
-        // 3. maps of the warps to the right of this one (warp+1 .. last)
-        Map warp_excl{1.0, 0.0};
-        for (int k = NW - 1; k > warp; --k) warp_excl = compose(Map{sA[k], sB[k]}, warp_excl);
-
-        // 4. incoming carry of the tile.  Common case (episodic data): the look-ahead window contains an episode
-        //    end, every thread reads the carry from shared memory and no second barrier is needed; thread 0
-        //    publishes the tile's inclusive value off the critical path.  Otherwise (CTA-uniform branch) thread 0
-        //    runs the decoupled look-back and the CTA waits for it.
-        const bool look_hit = (s_lookA == 0.0);
-        if (warp == 0) {
-            const Map tile = compose(Map{sA[0], sB[0]}, warp_excl);      // the same value in every lane of warp 0
-            double carry = 0.0;
-            if (lane == 0 && tile.A == 0.0) {       // an episode ends inside the tile: its inclusive value needs no carry
-                sc.incl[t] = tile.B;
-                st_release_i32(sc.flags + t, 2);
-            }
-            if (look_hit) {
-                carry = s_lookB;       // the value of the recurrence at the first transition right of the tile
-            } else if (t > 0) {
-                // decoupled look-back over the tiles to the right: lower tile ids, i.e. earlier iterations of
-                // co-resident CTAs (or lower block ids in the same iteration), which never wait on this one.  Inside a
-                // very long episode every tile waits for its predecessors; the chain of inclusive values advances 32
-                // tiles per memory round trip (warp-wide look-back) instead of one.
-                if (lane == 0 && tile.A != 0.0) {
+        // 3. incoming carry; publication for the left neighbour (see the kernel comment)
+        const bool publish = (__ballot_sync(0xffffffffu, tbits != 0u) & 0xffu) == 0u;     // no episode end in the first 128
+        const bool look_hit = (lookA == 0.0);
+        if (publish && tile.A == 0.0 && lane == 0) {      // an episode ends inside the tile: its inclusive value needs no carry
+            sc.incl[t] = tile.B;
+            st_release_i32(sc.flags + t, 2);
+        }
+        double carry = lookB;       // look-ahead hit: the value of the recurrence at the first transition right of the tile
+        if (!look_hit) {
+            carry = 0.0;
+            if (t > 0) {
+                // decoupled look-back over the tiles to the right: lower tile ids, i.e. earlier iterations of co-resident
+                // warps (or lower warp ids in the same iteration), which never wait on this one
+                if (publish && tile.A != 0.0 && lane == 0) {
                     sc.aggA[t] = tile.A; sc.aggB[t] = tile.B;
                     st_release_i32(sc.flags + t, 1);
                 }
                 carry = warp_lookback(sc, t, lane);
             }
-            if (lane == 0 && tile.A != 0.0) {
-                sc.incl[t] = __dadd_rn(tile.B, __dmul_rn(tile.A, carry));
-                st_release_i32(sc.flags + t, 2);
-            }
-            if (!look_hit && lane == 0) s_carry = carry;
         }
-        if (!look_hit) __syncthreads();
+        if (publish && tile.A != 0.0 && lane == 0) {
+            sc.incl[t] = __dadd_rn(tile.B, __dmul_rn(tile.A, carry));
+            st_release_i32(sc.flags + t, 2);
+        }
 
-        // 5. thread's incoming carry, then the reference's serial recurrence over its 16 items
-        double c = look_hit ? s_lookB : s_carry;
-        c = __dadd_rn(warp_excl.B, __dmul_rn(warp_excl.A, c));
-        c = __dadd_rn(lane_excl.B, __dmul_rn(lane_excl.A, c));
+        // 4. thread's incoming carry, then the reference's serial recurrence over its 16 items
+        double c = __dadd_rn(lane_excl.B, __dmul_rn(lane_excl.A, carry));
         // the left half starts from the value at item 8 = right-half map applied to the carry
         const double c_lo = __dadd_rn(Bh, __dmul_rn(Ah, c));
         // the rewards are re-read from the stage (the thread's own slot) instead of being held in 16 registers across
-        // the barrier and the look-back: the kernel runs at 64 registers per thread (4 CTAs per SM)
+        // the scan and the look-back: the kernel runs at 64 registers per thread (4 CTAs per SM)
 #pragma unroll
         for (int q = 0; q < SCAN_ITEMS / 4; ++q) {
             float4 v;
@@ -400,10 +382,12 @@ returns_scan_kernel(const float* __restrict__ rew, float* __restrict__ out, cons
 #pragma unroll
             for (int q = 0; q < SCAN_ITEMS / 4; ++q)
                 *reinterpret_cast<float4*>(wx + sx_off(lane, q)) = make_float4(r[4 * q], r[4 * q + 1], r[4 * q + 2], r[4 * q + 3]);
+            if (tile_stats != nullptr) {
 #pragma unroll
-            for (int i = 0; i < SCAN_ITEMS; ++i) { lsum += r[i]; lsq = fmaf(r[i], r[i], lsq); }
+                for (int i = 0; i < SCAN_ITEMS; ++i) { lsum += r[i]; lsq = fmaf(r[i], r[i], lsq); }
+            }
             __syncwarp();
-            float4* op = reinterpret_cast<float4*>(out + tile_base + (int64_t)warp * (32 * SCAN_ITEMS));
+            float4* op = reinterpret_cast<float4*>(out + tile_base);
 #pragma unroll
             for (int q = 0; q < SCAN_ITEMS / 4; ++q)
                 __stcs(op + q * 32 + lane, *reinterpret_cast<const float4*>(wx + sx_off(q * 8 + (lane >> 2), lane & 3)));
@@ -415,7 +399,7 @@ returns_scan_kernel(const float* __restrict__ rew, float* __restrict__ out, cons
             }
         }
 
-        // 6. K2 statistics of the returns: one {sum, sumsq} pair per warp (fp32 partials over the warp's 512 values,
+        // 5. K2 statistics of the returns: one {sum, sumsq} pair per warp tile (fp32 partials over its 512 values,
         //    Float64 from there on, folded in a fixed order by norm_finalize_kernel => deterministic)
         if (tile_stats != nullptr) {
 #pragma unroll
@@ -424,8 +408,8 @@ returns_scan_kernel(const float* __restrict__ rew, float* __restrict__ out, cons
                 lsq += __shfl_down_sync(0xffffffffu, lsq, d);
             }
             if (lane == 0) {
-                tile_stats[2 * ((int64_t)tile_idx * NW + warp)] = (double)lsum;
-                tile_stats[2 * ((int64_t)tile_idx * NW + warp) + 1] = (double)lsq;
+                tile_stats[2 * (int64_t)tile_idx] = (double)lsum;
+                tile_stats[2 * (int64_t)tile_idx + 1] = (double)lsq;
             }
         }
     }
@@ -477,8 +461,12 @@ norm_finalize_kernel(const double* __restrict__ tile_stats, int64_t tiles, int64
 
 }  // namespace
 
+// warp tiles of n transitions, rounded up to whole 4 096-transition groups (the K2 statistics keep one {sum, sumsq} pair per
+// warp tile of every group, so that norm_finalize / returns_stats see the same partition as before)
+static inline int64_t scan_warp_tiles(int64_t n) { return ceil_div(n > 0 ? n : 1, SCAN_TILE) * (SCAN_TILE / (32 * SCAN_ITEMS)); }
+
 size_t scan_scratch_bytes(int64_t n) {
-    int64_t tiles = ceil_div(n > 0 ? n : 1, SCAN_TILE);
+    int64_t tiles = scan_warp_tiles(n);
     return 16 + (size_t)round_up(tiles * 4, 16) + (size_t)tiles * 3 * sizeof(double);
 }
 
@@ -486,7 +474,7 @@ int launch_returns_scan(ppo_ctx* ctx, const float* reward_in, float* returns_out
                         double discount, int discount_is_f32, double* tile_stats, void* scratch) {
     PPO_REQUIRE(reward_in != returns_out, "returns scan runs out of place (the look-ahead reads its right neighbours' rewards)");
     if (n <= 0) return PPO_OK;
-    int64_t tiles = ceil_div(n, SCAN_TILE);
+    int64_t tiles = scan_warp_tiles(n);
     PPO_REQUIRE(tiles < (int64_t)1 << 30, "returns scan: too many tiles");
     ScanScratch sc = carve(scratch, tiles);
     PPO_CUDA(cudaMemsetAsync(scratch, 0, 16 + (size_t)round_up(tiles * 4, 16), ctx->stream));
@@ -494,14 +482,14 @@ int launch_returns_scan(ppo_ctx* ctx, const float* reward_in, float* returns_out
     double g8 = 1.0;
     for (int i = 0; i < SCAN_ITEMS / 2; ++i) g8 *= g;  // the same left-to-right product a per-item loop would form
     // persistent grid: every CTA must be co-resident (the look-back waits on lower tile ids)
-    const size_t smem = 2 * sizeof(ScanStage);
+    const size_t smem = 2 * SCAN_WARPS * sizeof(WarpStage);
     int occ = 0;
     const bool g1 = (g == 1.0);
     auto launch = [&](auto kern) -> int {
         PPO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         PPO_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, SCAN_THREADS, smem));
         PPO_REQUIRE(occ >= 1, "returns scan: kernel does not fit on an SM");
-        const int64_t grid = std::min<int64_t>(tiles, (int64_t)ctx->num_sms * occ);
+        const int64_t grid = std::min<int64_t>(ceil_div(tiles, SCAN_WARPS), (int64_t)ctx->num_sms * occ);
         kern<<<(unsigned)grid, SCAN_THREADS, smem, ctx->stream>>>(reward_in, returns_out, terminal, n, g, g8, (int)tiles, sc,
                                                                   tile_stats);
         return PPO_OK;

@@ -537,6 +537,11 @@ def test_variable_size_states_padded_like_the_reference(ctx):
     pol = P.Policy(nf, H, L, apa, ctx, weights=W, biases=b)
     dprobs = P.batch_action_probabilities(pol, P.StateData(feat, mask))
     assert np.all(dprobs[~np.isfinite(mask)] == 0.0)
+    # the padded tokens are stored (the buffer keeps the reference's padded layout) but the MLP never
+    # runs them: the fp16-split engine compacts every minibatch to the tokens that have an unmasked action
+    if pol.gemm_mode == P.GEMM_F16X3_TC:
+        live = int((~np.all(np.isneginf(mask.reshape(-1, apa)), axis=1)).sum())
+        assert pol.active_tokens() == live < n * nhe
     perm = np.random.default_rng(2).permutation(n) + 1
     got = P.step_epoch_(pol, P.Adam(1e-4), P.construct_dataset(buf), 0.05, cfg.B, 0.01, perm=perm)
     obuf = O.BufferRollouts(nf, nhe, apa)
