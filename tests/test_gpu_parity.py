@@ -402,6 +402,44 @@ def test_c1_testenv_collect_rollouts(ctx):
     pol.close(); rollouts.close()
 
 
+def test_ppo_iterate_outer_loop_on_the_testenv(ctx):
+    """``ppo_iterate!`` (src/train.jl:210-249) with the DEVICE policy in the loop: every iteration collects rollouts with
+    the current device weights (weight round trip through ppo_batch_action_probabilities), trains, and hands the loss
+    history to the evaluator's save_loss hook.  The TestEnv rewards action 1 only, so the policy's probability of action 1
+    must grow over the iterations; history lengths and the printed protocol follow the reference."""
+    import io
+
+    class Env:
+        def __init__(self): self.k, self.last = 0, 1
+        def state(self): return P.StateData(np.ones((1, 9), np.float32), np.zeros(3, np.float32))
+        def step_(self, a): self.k += 1; self.last = a
+        def reward(self): return 1.0 if self.last == 1 else 0.0
+        def is_terminal(self): return self.k >= 5
+        def reset_(self): self.k = 0
+
+    class Evaluator:
+        def __init__(self): self.calls, self.saved = 0, None
+        def __call__(self, policy, env, optimizer): self.calls += 1
+        def save_loss(self, loss): self.saved = {k: list(v) for k, v in loss.items()}
+
+    cfg = S.CONFIGS["c1"]
+    W, b = S.make_weights(cfg)
+    pol = P.Policy(cfg.nf, cfg.H, cfg.L, cfg.apa, ctx, weights=W, biases=b)
+    env, ev, out = Env(), Evaluator(), io.StringIO()
+    from ppo_b200 import collect_rollouts as CR
+    CR.seed_sampling(5)
+    p_before = P.action_probabilities(pol, env.state())[0]
+    loss = P.ppo_iterate_(pol, env, P.Adam(3e-3), 40, 50, 3, ev, 4, 1.0, 0.2, 0.0,
+                          rollouts_factory=lambda: P.DeviceRollouts(9, 1, 3, 256, ctx), out=out)
+    p_after = P.action_probabilities(pol, env.state())[0]
+    assert ev.calls == 3 and ev.saved == loss
+    assert len(loss["ppo"]) == len(loss["entropy"]) == len(loss["lr"]) == 12 and all(lr == 3e-3 for lr in loss["lr"])
+    text = out.getvalue()
+    assert text.count("PPO ITERATION : ") == 3 and text.count("EPOCH : ") == 12
+    assert np.all(np.isfinite(loss["ppo"])) and p_after > p_before + 0.02, (p_before, p_after)
+    pol.close()
+
+
 def test_advantage_normalisation_extension(ctx):
     cfg = S.CONFIGS["t1"]
     data, old, buf, obuf = _filled(ctx, cfg)
