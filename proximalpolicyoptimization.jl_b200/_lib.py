@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libppo_b200.so")
+# PPO_B200_LIB: an alternative build of the same library (A/B measurements of kernel variants)
+LIB_PATH = os.environ.get("PPO_B200_LIB") or os.path.join(_HERE, "libppo_b200.so")
 
 c_i64, c_u64, c_int, c_dbl, c_flt = C.c_int64, C.c_uint64, C.c_int, C.c_double, C.c_float
 vp = C.c_void_p
