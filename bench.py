@@ -131,7 +131,8 @@ def workload(args):
         "parallelism": f"dp{world}" if world > 1 else "single",
         "grad_exchange": (("nccl all-reduce" if os.environ.get("PPO_B200_NO_P2P", "0") == "1" else
                            "nvlink peer memory, fused into the Adam kernel") if world > 1 else None),
-        "host_features": {"i8": "int8 (ppo_buffer_append_i8)", "f32": "float32 (ppo_buffer_append)"}[args.e2e_feat],
+        "host_features": {"i8": "int8", "f32": "float32"}[args.e2e_feat] + " features, " +
+                         {"bits": "1-bit action masks (ppo_buffer_append_packed)", "f32": "float32 action masks"}[args.e2e_mask],
         "l2": "step inputs exceed L2; per-kernel timings flush L2 between launches (write 256 MB, then read 256 MB)",
     }
     return cfg, B_local, config
@@ -247,12 +248,14 @@ def make_data(cfg, P, S, ctx, W, b, rank, feat_dtype=np.int8, cheap_old=False):
     old = alloc((cfg.N,), np.float32)
     old[...] = S.make_old_probs(cfg_r, sel)
     data["old"] = old
+    # the same masks as one bit per action (what ppo_buffer_append_packed takes; a Julia BitMatrix's chunks)
+    data["mask_bits"] = P.pack_action_mask(data["mask"], out=alloc((-(-cfg.N * cfg.A // 64),), np.uint64))
     log(f"[rank {rank}] synthetic data for {cfg.name} ready in {time.perf_counter() - t0:.1f} s")
     return data
 
 
-def host_bytes_per_transition(cfg, feat_dtype):
-    return np.dtype(feat_dtype).itemsize * cfg.nf * cfg.nhe + 4 * cfg.A + 8 + 4 + 4 + 1
+def host_bytes_per_transition(cfg, feat_dtype, mask_bits=False):
+    return np.dtype(feat_dtype).itemsize * cfg.nf * cfg.nhe + (cfg.A / 8.0 if mask_bits else 4 * cfg.A) + 8 + 4 + 4 + 1
 
 
 class _StdoutToStderr:
@@ -354,7 +357,7 @@ class Harness:
 
 
 def run_update_legs(h, cfg, B_local, gemm_mode, data, W, b, steps, warmup, feat_key="feat", sample_clocks=True, e2e=True,
-                    compact=True):
+                    compact=True, mask_key="mask"):
     """resident + end-to-end legs of one workload; returns a dict of raw measurements.  compact: token compaction (the
     library's default: the MLP skips tokens all of whose actions are masked; exact zeros either way)"""
     P = h.P
@@ -368,7 +371,7 @@ def run_update_legs(h, cfg, B_local, gemm_mode, data, W, b, steps, warmup, feat_
 
     def fill():
         buf.clear()
-        buf.append(data[feat_key], data["mask"], data["old"], data["action"], data["reward"], data["terminal"])
+        buf.append(data[feat_key], data[mask_key], data["old"], data["action"], data["reward"], data["terminal"])
 
     def update(seed):
         P.compute_state_value_(buf, GAMMA)
@@ -507,7 +510,8 @@ def run_c2(h, args, gemm_mode):
     out = {}
     steps = max(1, min(args.steps, 5))
     for B in (32, 4096):
-        r = run_update_legs(h, cfg, B, gemm_mode, data, W, b, steps, 2, sample_clocks=False)
+        r = run_update_legs(h, cfg, B, gemm_mode, data, W, b, steps, 2, sample_clocks=False,
+                            mask_key="mask_bits" if args.e2e_mask == "bits" else "mask")
         nb = r["nbatches"]
         out[f"c2_b{B}"] = {"value": round(cfg.N / (r["ms_step"] * 1e-3), 1), "e2e": round(cfg.N / (r["ms_e2e"] * 1e-3), 1),
                            "ms_per_step": round(r["ms_step"], 3), "us_per_minibatch": round(1e3 * r["ms_step"] / nb, 2),
@@ -685,7 +689,9 @@ def _run_ours(args):
     W, b = S.make_weights(cfg)
     data = make_data(cfg, P, S, h.ctx, W, b, rank, feat_dtype, cheap_old=args.profile)
 
-    main = run_update_legs(h, cfg, B_local, gemm_mode, data, W, b, args.steps, args.warmup, e2e=not args.profile)
+    mask_key = "mask_bits" if args.e2e_mask == "bits" else "mask"
+    main = run_update_legs(h, cfg, B_local, gemm_mode, data, W, b, args.steps, args.warmup, e2e=not args.profile,
+                           mask_key=mask_key)
     value = cfg.N * world / (main["ms_step"] * 1e-3)
     if args.profile:
         line = None
@@ -697,7 +703,7 @@ def _run_ours(args):
         h.ctx.close()
         return line
     e2e = {"value": cfg.N * world / (main["ms_e2e"] * 1e-3), "unit": UNIT,
-           "h2d_bytes_per_step": cfg.N * host_bytes_per_transition(cfg, feat_dtype),
+           "h2d_bytes_per_step": int(cfg.N * host_bytes_per_transition(cfg, feat_dtype, args.e2e_mask == "bits")),
            "d2h_bytes_per_step": 16 * main["nbatches"], "ms_per_step": main["ms_e2e"], "steps": args.steps}
     # token compaction is the library default; the same steps with every token pushed through the MLP (what the
     # reference does with fully masked tokens) are timed beside it
@@ -827,6 +833,8 @@ def main():
                     help="weak: a C3-sized shard per GPU (default; = config C4 at N=8); strong: config C4 as written, "
                          "8 388 608 transitions in total at any N")
     ap.add_argument("--e2e-feat", default="i8", choices=["i8", "f32"], help="dtype of the host-side features of the e2e leg")
+    ap.add_argument("--e2e-mask", default="bits", choices=["bits", "f32"],
+                    help="host-side action masks: one bit per action (ppo_buffer_append_packed) or Float32 0 / -Inf")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -98,6 +98,14 @@ int ppo_buffer_append_i8(ppo_buf* buf, int64_t n, const int8_t* feat, const floa
 int ppo_buffer_append_i16(ppo_buf* buf, int64_t n, const int16_t* feat, const float* mask,
                           const int64_t* action, const float* old_prob, const float* reward,
                           const uint8_t* terminal);
+/* same, with the narrowest host representation of both big arrays: features of feat_elem_bytes per element (1 = Int8,
+ * 2 = Int16, 4 = Float32, 8 = Int64) and the action mask as ONE BIT per action (1 = allowed = 0f0, 0 = masked = -Inf32),
+ * bit (a + A*s) of the stream = bit ((a + A*s) & 63) of word (a + A*s) >> 6 -- the `chunks` of the Julia
+ * BitMatrix `isfinite.(action_mask)` of size (A, n).  The masks of test/quad_game_utilities.jl:39-44 only ever hold
+ * 0f0 and -Inf32, so nothing is lost; C3 moves 1.09 GB per million transitions instead of 1.36 GB (Int8 + Float32 mask)
+ * or 4.58 GB (Float32 + Float32).  mask_bits holds ceil(n*A/64) words. */
+int ppo_buffer_append_packed(ppo_buf* buf, int64_t n, const void* feat, int feat_elem_bytes, const uint64_t* mask_bits,
+                             const int64_t* action, const float* old_prob, const float* reward, const uint8_t* terminal);
 /* Base.length, :40-48 */
 int64_t ppo_buffer_length(ppo_buf* buf);
 int ppo_buffer_clear(ppo_buf* buf);

@@ -8,7 +8,7 @@ from ._lib import PPOError, LIB_PATH, load as load_library
 from .context import Context, default_context
 from .rollout_buffer import (DeviceRollouts, DeviceDataset, StateData, batch_state, update_, length,
                              compute_state_value_, permute_, shuffle_, construct_dataset, get_sample, get_batch,
-                             pad_vertex_scores, pad_action_mask, prepare_state_data_for_batching_)
+                             pad_vertex_scores, pad_action_mask, prepare_state_data_for_batching_, pack_action_mask)
 from .collect_rollouts import (collect_step_data_, collect_episode_data_, collect_rollouts_, compute_returns)
 from .policy import Policy, Adam, Optimiser, action_probabilities, batch_action_probabilities, \
     number_of_actions_per_state, batch_sample_actions

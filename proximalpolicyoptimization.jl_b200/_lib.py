@@ -40,6 +40,7 @@ SIGNATURES = {
     "ppo_buffer_append_i64": (c_int, [vp, c_i64, PI64, PF, PI64, PF, PF, PU8]),
     "ppo_buffer_append_i8": (c_int, [vp, c_i64, C.POINTER(C.c_int8), PF, PI64, PF, PF, PU8]),
     "ppo_buffer_append_i16": (c_int, [vp, c_i64, C.POINTER(C.c_int16), PF, PI64, PF, PF, PU8]),
+    "ppo_buffer_append_packed": (c_int, [vp, c_i64, vp, c_int, C.POINTER(C.c_uint64), PI64, PF, PF, PU8]),
     "ppo_buffer_length": (c_i64, [vp]),
     "ppo_buffer_clear": (c_int, [vp]),
     "ppo_compute_returns": (c_int, [vp, c_dbl, c_int]),

@@ -330,19 +330,22 @@ int grow_buffer(ppo_buf* buf, int64_t need) {
 
 // feat_bytes: element size of the host features: 4 = Float32 (copied as is), 8 = Int64, 1 / 2 = Int8 / Int16 (staged in
 // scratch, widened to Float32 on the device; exact)
+// mask_bits != nullptr: the action mask as one bit per action (1 = allowed) instead of Float32 0 / -Inf
 int append_common(ppo_buf* buf, int64_t n, const void* feat, int feat_bytes, const float* mask, const int64_t* action,
-                  const float* old_prob, const float* reward, const uint8_t* terminal) {
+                  const float* old_prob, const float* reward, const uint8_t* terminal, const uint64_t* mask_bits = nullptr) {
     ppo_ctx* ctx = buf->ctx;
     PPO_TRY(use(ctx));
     PPO_REQUIRE(n >= 0, "append: n < 0");
     if (n == 0) return PPO_OK;
-    PPO_REQUIRE(feat && mask && action && old_prob && reward && terminal, "append: null input");
+    PPO_REQUIRE(feat && (mask || mask_bits) && action && old_prob && reward && terminal, "append: null input");
     if (buf->n + n > buf->cap) PPO_TRY(grow_buffer(buf, buf->n + n));
     const int64_t fe = (int64_t)buf->nf * buf->nhe;
     const int64_t off = buf->n;
     const size_t act_bytes = (size_t)round_up(n * 8, 64);
     size_t scratch = 64 + act_bytes;
-    if (feat_bytes != 4) scratch += (size_t)n * fe * feat_bytes;
+    const size_t feat_scratch = feat_bytes != 4 ? (size_t)round_up(n * fe * feat_bytes, 64) : 0;
+    const size_t bit_words = mask_bits != nullptr ? (size_t)ceil_div(n * buf->A, 64) : 0;
+    scratch += feat_scratch + bit_words * 8;
     PPO_TRY(ensure_scratch(ctx, scratch));
     int* d_bad = (int*)ctx->d_scratch;
     int64_t* d_act = (int64_t*)((char*)ctx->d_scratch + 64);
@@ -355,7 +358,13 @@ int append_common(ppo_buf* buf, int64_t n, const void* feat, int feat_bytes, con
     } else {
         PPO_TRY(h2d(ctx, buf->feat + off * fe, feat, (size_t)n * fe * 4));
     }
-    PPO_TRY(h2d(ctx, buf->mask + off * buf->A, mask, (size_t)n * buf->A * 4));
+    if (mask_bits != nullptr) {
+        uint64_t* d_bits = (uint64_t*)((char*)ctx->d_scratch + 64 + act_bytes + feat_scratch);
+        PPO_TRY(h2d(ctx, d_bits, mask_bits, bit_words * 8));
+        PPO_TRY(launch_mask_from_bits(ctx, d_bits, buf->mask + off * buf->A, n * buf->A));
+    } else {
+        PPO_TRY(h2d(ctx, buf->mask + off * buf->A, mask, (size_t)n * buf->A * 4));
+    }
     PPO_TRY(h2d(ctx, buf->old_prob + off, old_prob, (size_t)n * 4));
     PPO_TRY(h2d(ctx, buf->reward + off, reward, (size_t)n * 4));
     PPO_TRY(h2d(ctx, buf->terminal + off, terminal, (size_t)n));
@@ -557,6 +566,15 @@ int ppo_buffer_append_i8(ppo_buf* buf, int64_t n, const int8_t* feat, const floa
                          const float* old_prob, const float* reward, const uint8_t* terminal) {
     PPO_REQUIRE(buf != nullptr, "null buffer");
     return append_common(buf, n, feat, 1, mask, action, old_prob, reward, terminal);
+}
+
+int ppo_buffer_append_packed(ppo_buf* buf, int64_t n, const void* feat, int feat_elem_bytes, const uint64_t* mask_bits,
+                             const int64_t* action, const float* old_prob, const float* reward, const uint8_t* terminal) {
+    PPO_REQUIRE(buf != nullptr, "append: null buffer");
+    PPO_REQUIRE(feat_elem_bytes == 1 || feat_elem_bytes == 2 || feat_elem_bytes == 4 || feat_elem_bytes == 8,
+                "append_packed: feature element size %d (1 = Int8, 2 = Int16, 4 = Float32, 8 = Int64)", feat_elem_bytes);
+    PPO_REQUIRE(mask_bits != nullptr, "append_packed: null mask bits");
+    return append_common(buf, n, feat, feat_elem_bytes, nullptr, action, old_prob, reward, terminal, mask_bits);
 }
 
 int ppo_buffer_append_i16(ppo_buf* buf, int64_t n, const int16_t* feat, const float* mask, const int64_t* action,

@@ -195,6 +195,7 @@ int launch_i64_to_f32(ppo_ctx* ctx, const int64_t* src, float* dst, int64_t n);
 int launch_narrow_to_f32(ppo_ctx* ctx, const void* src, int elem_bytes /* 1: int8, 2: int16 */, float* dst, int64_t n);
 int launch_normalize_bool(ppo_ctx* ctx, uint8_t* t, int64_t n);
 int launch_step_advance(ppo_ctx* ctx, int* d_step);
+int launch_mask_from_bits(ppo_ctx* ctx, const uint64_t* bits, float* mask, int64_t n);
 
 // loss.cu (K6)
 int64_t loss_num_blocks(int64_t nb, int A);

@@ -264,6 +264,14 @@ narrow_to_f32_kernel(const T* __restrict__ s, float* __restrict__ d, int64_t n) 
     if (blockIdx.x == 0 && tail < n) d[tail] = (float)s[tail];      // < 16 leftover elements
 }
 
+// action mask from one bit per action (1 = allowed -> 0.0f, 0 = masked -> -Inf32): bit i of the stream is bit (i & 63)
+// of word i >> 6 (the layout of a Julia BitMatrix's chunks)
+__global__ void __launch_bounds__(256)
+mask_from_bits_kernel(const uint64_t* __restrict__ bits, float* __restrict__ mask, int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        mask[i] = ((__ldg(bits + (i >> 6)) >> (i & 63)) & 1ull) ? 0.0f : -INFINITY;
+}
+
 // element-wise variant for a destination that is not 16-byte aligned (an append at an odd element offset)
 template <typename T>
 __global__ void __launch_bounds__(256)
@@ -369,6 +377,14 @@ int launch_normalize_bool(ppo_ctx* ctx, uint8_t* t, int64_t n) {
 int launch_i64_to_f32(ppo_ctx* ctx, const int64_t* src, float* dst, int64_t n) {
     if (n <= 0) return PPO_OK;
     i64_to_f32_kernel<<<grid_for(ctx, n, 256), 256, 0, ctx->stream>>>(src, dst, n);
+    ctx->launches += 1;
+    PPO_CUDA(cudaGetLastError());
+    return PPO_OK;
+}
+
+int launch_mask_from_bits(ppo_ctx* ctx, const uint64_t* bits, float* mask, int64_t n) {
+    if (n <= 0) return PPO_OK;
+    mask_from_bits_kernel<<<grid_for(ctx, n, 256, 16), 256, 0, ctx->stream>>>(bits, mask, n);
     ctx->launches += 1;
     PPO_CUDA(cudaGetLastError());
     return PPO_OK;

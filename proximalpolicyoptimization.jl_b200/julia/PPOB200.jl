@@ -67,9 +67,17 @@ function flush!(b::DeviceRollouts)
         if all(x -> x == round(x) && -128 <= x <= 127, b.feat)
             # vertex scores / degrees are small integers (test/quad_game_utilities.jl:50-56): a quarter of the bytes
             f8 = Int8.(b.feat)
-            check(ccall((:ppo_buffer_append_i8, lib), Cint,
-                        (Ptr{Cvoid}, Int64, Ptr{Int8}, Ptr{Float32}, Ptr{Int64}, Ptr{Float32}, Ptr{Float32}, Ptr{UInt8}),
-                        b.h, n, f8, b.mask, b.act, b.prob, b.rew, b.term))
+            if all(x -> x == 0f0 || x == -Inf32, b.mask)
+                # ... and the masks only hold 0f0 / -Inf32 (:39-44): one bit per action (BitVector chunks, 1 = allowed)
+                bits = BitVector(isfinite.(b.mask))
+                check(ccall((:ppo_buffer_append_packed, lib), Cint,
+                            (Ptr{Cvoid}, Int64, Ptr{Cvoid}, Cint, Ptr{UInt64}, Ptr{Int64}, Ptr{Float32}, Ptr{Float32}, Ptr{UInt8}),
+                            b.h, n, f8, 1, bits.chunks, b.act, b.prob, b.rew, b.term))
+            else
+                check(ccall((:ppo_buffer_append_i8, lib), Cint,
+                            (Ptr{Cvoid}, Int64, Ptr{Int8}, Ptr{Float32}, Ptr{Int64}, Ptr{Float32}, Ptr{Float32}, Ptr{UInt8}),
+                            b.h, n, f8, b.mask, b.act, b.prob, b.rew, b.term))
+            end
         else
             check(ccall((:ppo_buffer_append, lib), Cint,
                         (Ptr{Cvoid}, Int64, Ptr{Float32}, Ptr{Float32}, Ptr{Int64}, Ptr{Float32}, Ptr{Float32}, Ptr{UInt8}),

@@ -142,9 +142,13 @@ class DeviceRollouts:
 
     def append(self, feat, mask, action_probability, action, reward, terminal):
         """Batched ``update!``: n transitions at once.  feat [n, nhe, nf] float32, int64 (the reference's
-        ``Matrix{Int64}`` scores) or int8 / int16 (narrowed by the caller: exact, 4x / 2x fewer host->device bytes)."""
+        ``Matrix{Int64}`` scores) or int8 / int16 (narrowed by the caller: exact, 4x / 2x fewer host->device bytes).
+        mask: float32 [n, A] of 0 / -Inf, or packed bits (``pack_action_mask``: uint64 words, one bit per action,
+        1 = allowed; 32x fewer bytes)."""
         feat = np.asarray(feat)
         n = feat.shape[0] if feat.ndim == 3 else feat.size // (self.nhe * self.nf)
+        if isinstance(mask, np.ndarray) and mask.dtype == np.uint64:
+            return self._append_packed(feat, n, mask, action_probability, action, reward, terminal)
         mask = np.ascontiguousarray(mask, np.float32).reshape(n, self.A)
         act = np.ascontiguousarray(action, np.int64).reshape(n)
         prob = np.ascontiguousarray(action_probability, np.float32).reshape(n)
@@ -163,6 +167,21 @@ class DeviceRollouts:
             _lib.check(lib.ppo_buffer_append(self.handle, n, _lib.ptr(f, C.c_float), _lib.ptr(mask, C.c_float),
                                              _lib.ptr(act, C.c_int64), _lib.ptr(prob, C.c_float),
                                              _lib.ptr(rew, C.c_float), _lib.ptr(term, C.c_uint8)))
+
+    def _append_packed(self, feat, n, mask_bits, action_probability, action, reward, terminal):
+        words = -(-n * self.A // 64)
+        bits = np.ascontiguousarray(mask_bits, np.uint64).reshape(-1)
+        assert bits.size == words, (bits.size, words)
+        if feat.dtype not in (np.dtype(np.int8), np.dtype(np.int16), np.dtype(np.int64)):
+            feat = feat.astype(np.float32, copy=False)
+        f = np.ascontiguousarray(feat).reshape(n, self.nhe, self.nf)
+        act = np.ascontiguousarray(action, np.int64).reshape(n)
+        prob = np.ascontiguousarray(action_probability, np.float32).reshape(n)
+        rew = np.ascontiguousarray(reward, np.float32).reshape(n)
+        term = np.ascontiguousarray(np.asarray(terminal).astype(np.uint8)).reshape(n)
+        _lib.check(_lib.load().ppo_buffer_append_packed(
+            self.handle, n, f.ctypes.data_as(C.c_void_p), f.dtype.itemsize, _lib.ptr(bits, C.c_uint64),
+            _lib.ptr(act, C.c_int64), _lib.ptr(prob, C.c_float), _lib.ptr(rew, C.c_float), _lib.ptr(term, C.c_uint8)))
 
     def __len__(self):
         """``Base.length`` — :40-48."""
@@ -285,6 +304,20 @@ class DeviceDataset:
         if isinstance(idx, (list, tuple, np.ndarray)):
             return get_batch(self, idx)
         raise TypeError(f"Dataset index should be Int or Array, got {type(idx)}")
+
+
+def pack_action_mask(mask, out=None):
+    """0 / -Inf action masks [n, A] -> one bit per action (1 = allowed), little-endian bits in uint64 words: the layout
+    of ``BitMatrix(isfinite.(action_mask)).chunks`` in Julia, accepted by ``DeviceRollouts.append`` /
+    ``ppo_buffer_append_packed``."""
+    allowed = np.isfinite(np.asarray(mask)).reshape(-1)
+    words = -(-allowed.size // 64)
+    by = np.packbits(allowed, bitorder="little")
+    if out is None:
+        out = np.zeros(words, np.uint64)
+    out.view(np.uint8)[:by.size] = by
+    out.view(np.uint8)[by.size:] = 0
+    return out
 
 
 def get_sample(dataset: DeviceDataset, idx):

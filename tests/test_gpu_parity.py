@@ -174,6 +174,29 @@ def test_integer_feature_append_is_exact(ctx, dtype):
     buf.close(); ref.close()
 
 
+def test_packed_append_equals_the_float_mask_append(ctx):
+    """ppo_buffer_append_packed (Int8 features + one bit per action) fills the buffer with exactly the bytes of the
+    Float32-mask append, also when a second append starts at an offset that is not a multiple of 64 actions"""
+    rng = np.random.default_rng(8)
+    nf, nhe, apa = 8, 3, 4                          # A = 12
+    out = {}
+    for packed in (False, True):
+        buf = P.DeviceRollouts(nf, nhe, apa, 64, ctx)
+        r = np.random.default_rng(8)
+        for n in (37, 5, 100):
+            f = r.integers(-3, 9, (n, nhe, nf)).astype(np.int8)
+            m = np.where(r.random((n, nhe * apa)) < 0.4, -np.inf, 0.0).astype(np.float32)
+            m[:, 0] = 0.0
+            a = S.make_actions(r, m)
+            args = (r.random(n).astype(np.float32), a, r.integers(-4, 5, n).astype(np.float32), r.random(n) < 0.1)
+            buf.append(f, P.pack_action_mask(m) if packed else m, *args)
+        out[packed] = buf.read()
+        buf.close()
+    for k in out[False]:
+        assert np.array_equal(out[False][k], out[True][k]), k
+    assert np.isneginf(out[True]["mask"]).sum() > 0 and set(np.unique(out[True]["mask"])) == {-np.inf, 0.0}
+
+
 def test_gather_variants_agree_bit_exact(ctx):
     # LDG/STG path (variant 0) and TMA bulk-copy ring (variant 1, cp.async.bulk) against the oracle
     import ctypes as C

@@ -135,3 +135,18 @@ def test_p2p_gradient_exchange_is_a_noop_for_one_rank():
             assert D.enable_p2p_gradients(policy=None) is False
         finally:
             dist.destroy_process_group()
+
+
+def test_pack_action_mask_is_the_julia_bitmatrix_layout():
+    """bit (a + A*s) of the stream = bit ((a + A*s) & 63) of word (a + A*s) >> 6, 1 = allowed: what
+    ``BitMatrix(isfinite.(action_mask)).chunks`` holds for an (A, n) mask in Julia (column-major, little-endian bits)"""
+    import ppo_b200 as P
+    rng = np.random.default_rng(4)
+    n, A = 37, 12                                  # n*A = 444: not a multiple of 64
+    mask = np.where(rng.random((n, A)) < 0.4, -np.inf, 0.0).astype(np.float32)
+    bits = P.pack_action_mask(mask)
+    assert bits.dtype == np.uint64 and bits.size == 7
+    flat = np.isfinite(mask).reshape(-1)
+    for k in range(n * A):
+        assert ((int(bits[k >> 6]) >> (k & 63)) & 1) == int(flat[k])
+    assert int(bits[6]) >> (444 - 384) == 0        # padding bits are zero

@@ -16,7 +16,7 @@ JULIA = os.path.join(ROOT, "proximalpolicyoptimization.jl_b200", "julia", "PPOB2
 JL = {
     "Cint": "i32", "Int64": "i64", "UInt64": "u64", "Cdouble": "f64", "Cfloat": "f32", "Cstring": "cstr",
     "Ptr{Cvoid}": "ptr", "Ref{Ptr{Cvoid}}": "pptr", "Ptr{Float32}": "p_f32", "Ptr{Int64}": "p_i64", "Ptr{UInt8}": "p_u8",
-    "Ptr{Int8}": "p_i8", "Ptr{Int16}": "p_i16", "Ptr{Cint}": "p_i32", "Ref{Cint}": "p_i32", "Ref{Int64}": "p_i64",
+    "Ptr{Int8}": "p_i8", "Ptr{Int16}": "p_i16", "Ptr{UInt64}": "p_u64", "Ptr{Cint}": "p_i32", "Ref{Cint}": "p_i32", "Ref{Int64}": "p_i64",
     "Ref{Cdouble}": "p_f64", "Ptr{Cdouble}": "p_f64", "Ptr{Ptr{Float32}}": "pp_f32",
 }
 
@@ -37,10 +37,10 @@ def c_class(t):
         return "pptr"
     if t in ("float**", "float* *"):
         return "pp_f32"
-    m = re.fullmatch(r"(float|double|int|int8_t|int16_t|int64_t|uint8_t)\*", t)
+    m = re.fullmatch(r"(float|double|int|int8_t|int16_t|int64_t|uint8_t|uint64_t)\*", t)
     if m:
         return "p_" + {"float": "f32", "double": "f64", "int": "i32", "int8_t": "i8", "int16_t": "i16", "int64_t": "i64",
-                       "uint8_t": "u8"}[m.group(1)]
+                       "uint8_t": "u8", "uint64_t": "u64"}[m.group(1)]
     raise ValueError(f"unclassified C type {t!r}")
 
 
