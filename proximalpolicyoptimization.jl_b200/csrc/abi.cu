@@ -158,10 +158,10 @@ int refresh_engine_weights(ppo_policy* p) {
 
 // forward through all Dense layers: act[l] for l = 1..L  (act[L] = logits, linear).  mask: the action mask the logits
 // will be added to (lets the fp16-split engine skip fully masked tokens), or nullptr
-int policy_forward(ppo_policy* p, const float* X, int64_t M, const float* mask) {
+int policy_forward(ppo_policy* p, const float* X, int64_t M, const float* mask, const unsigned* feat_bound = nullptr) {
     ppo_ctx* ctx = p->ctx;
     const int L = p->L;
-    if (p->gemm_mode == PPO_GEMM_F16X3_TC) return f16_forward(p, X, M, mask);
+    if (p->gemm_mode == PPO_GEMM_F16X3_TC) return f16_forward(p, X, M, mask, feat_bound);
     const float* in = X;
     for (int l = 0; l < L; ++l) {
         const int K = p->dims[l], N = p->dims[l + 1];
@@ -182,10 +182,10 @@ int policy_forward(ppo_policy* p, const float* X, int64_t M, const float* mask) 
 }
 
 // backward from p->dlogits: fills p->grads (Flux.params order)
-int policy_backward(ppo_policy* p, const float* X, int64_t M) {
+int policy_backward(ppo_policy* p, const float* X, int64_t M, bool dl_stat_ready = false) {
     ppo_ctx* ctx = p->ctx;
     const int L = p->L;
-    if (p->gemm_mode == PPO_GEMM_F16X3_TC) return f16_backward(p, M);
+    if (p->gemm_mode == PPO_GEMM_F16X3_TC) return f16_backward(p, M, dl_stat_ready);
     const bool tc = p->gemm_mode != PPO_GEMM_FP32_SIMT;
     const float* delta = p->dlogits;
     int pp = 0;
@@ -230,11 +230,13 @@ int step_core(ppo_policy* p, ppo_opt* opt, const ppo_batch& bt, int64_t nb, int 
     const int64_t M = nb * nhe;
     PPO_TRY(ensure_workspace(p, M));
     PPO_TRY(ensure_loss_buffers(p, nb, A, slot + 1));
-    PPO_TRY(policy_forward(p, bt.feat, M, bt.mask));
+    PPO_TRY(policy_forward(p, bt.feat, M, bt.mask, bt.feat_bound));
+    // (fp16-split engine: the loss kernel also leaves max |dlogits| where the backward pass plans its scales from)
+    unsigned* dl_stat = p->gemm_mode == PPO_GEMM_F16X3_TC ? f16_dlogits_stat(p) : nullptr;
     PPO_TRY(launch_loss(ctx, p->act[L], bt.mask, bt.action, bt.old_prob, bt.adv, nb, A, epsilon, entropy_weight,
                         inv_nb_global, p->dlogits, p->d_loss_partials, p->d_loss_hist + (d_step ? 0 : 2 * slot), nullptr,
-                        d_step));
-    PPO_TRY(policy_backward(p, bt.feat, M));
+                        d_step, dl_stat));
+    PPO_TRY(policy_backward(p, bt.feat, M, dl_stat != nullptr));
     // fp16-split engine: optimiser step, weight statistics, scales, operand copies and the minibatch counter in one launch
     const bool fused = opt != nullptr && p->gemm_mode == PPO_GEMM_F16X3_TC;
     if (ctx->nccl_comm != nullptr && ctx->nranks > 1 && p2p_active(p)) {
@@ -274,6 +276,7 @@ int gather_into(ppo_buf* buf, ppo_batch& bt, const int* d_index, int64_t count, 
     a.feat_out = bt.feat; a.mask_out = bt.mask; a.action_out = bt.action; a.prob_out = bt.old_prob;
     a.adv_out = bt.adv;
     a.norm = buf->normalize ? buf->d_norm : nullptr;
+    bt.feat_bound = buf->d_feat_absmax;       // a bound of every row this gather can deliver
     return launch_gather(buf->ctx, a, variant);
 }
 
@@ -353,10 +356,16 @@ int append_common(ppo_buf* buf, int64_t n, const void* feat, int feat_bytes, con
     if (feat_bytes != 4) {
         void* d_f = (char*)ctx->d_scratch + 64 + act_bytes;
         PPO_TRY(h2d(ctx, d_f, feat, (size_t)n * fe * feat_bytes));
-        if (feat_bytes == 8) PPO_TRY(launch_i64_to_f32(ctx, (const int64_t*)d_f, buf->feat + off * fe, n * fe));
-        else PPO_TRY(launch_narrow_to_f32(ctx, d_f, feat_bytes, buf->feat + off * fe, n * fe));
+        // (the buffer keeps max |feature| of everything it holds: the fp16-split engine's bound for any minibatch)
+        if (feat_bytes == 8) {
+            PPO_TRY(launch_i64_to_f32(ctx, (const int64_t*)d_f, buf->feat + off * fe, n * fe));
+            PPO_TRY(launch_absmax_f32(ctx, buf->feat + off * fe, n * fe, buf->d_feat_absmax));
+        } else {
+            PPO_TRY(launch_narrow_to_f32(ctx, d_f, feat_bytes, buf->feat + off * fe, n * fe, buf->d_feat_absmax));
+        }
     } else {
         PPO_TRY(h2d(ctx, buf->feat + off * fe, feat, (size_t)n * fe * 4));
+        PPO_TRY(launch_absmax_f32(ctx, buf->feat + off * fe, n * fe, buf->d_feat_absmax));
     }
     if (mask_bits != nullptr) {
         uint64_t* d_bits = (uint64_t*)((char*)ctx->d_scratch + 64 + act_bytes + feat_scratch);
@@ -529,9 +538,15 @@ int ppo_buffer_create(ppo_ctx* ctx, int64_t capacity, int nf, int nhe, int apa, 
         (s = dev_alloc(&b->terminal, (size_t)cap16)) != PPO_OK ||
         (s = dev_alloc(&b->perm, (size_t)capacity)) != PPO_OK ||
         (s = dev_alloc(&b->d_norm, 2)) != PPO_OK ||
+        (s = dev_alloc(&b->d_feat_absmax, 1)) != PPO_OK ||
         (s = dev_alloc(&b->d_tile_stats, (size_t)2 * SCAN_STATS_PER_TILE * ceil_div(capacity, SCAN_TILE))) != PPO_OK) {
         ppo_buffer_destroy(b);
         return s;
+    }
+    if (cudaMemsetAsync(b->d_feat_absmax, 0, sizeof(unsigned), ctx->stream) != cudaSuccess) {
+        ppo_buffer_destroy(b);
+        set_error("buffer_create: memset failed");
+        return PPO_ERR_CUDA;
     }
     *out = b;
     return PPO_OK;
@@ -542,7 +557,7 @@ int ppo_buffer_destroy(ppo_buf* b) {
     cudaSetDevice(b->ctx->device);
     cudaStreamSynchronize(b->ctx->stream);
     dev_free(b->feat); dev_free(b->mask); dev_free(b->action); dev_free(b->old_prob); dev_free(b->reward);
-    dev_free(b->terminal); dev_free(b->perm); dev_free(b->reward_saved); dev_free(b->reward_alt); dev_free(b->d_norm); dev_free(b->d_tile_stats);
+    dev_free(b->terminal); dev_free(b->perm); dev_free(b->reward_saved); dev_free(b->reward_alt); dev_free(b->d_norm); dev_free(b->d_tile_stats); dev_free(b->d_feat_absmax);
     free_batch(b->batch);
     ppo_ctx* ctx = b->ctx;
     delete b;
@@ -591,6 +606,8 @@ int ppo_buffer_clear(ppo_buf* buf) {
     buf->perm_len = 0;
     buf->stats_valid = false;
     buf->returns_valid = false;
+    PPO_TRY(use(buf->ctx));
+    PPO_CUDA(cudaMemsetAsync(buf->d_feat_absmax, 0, sizeof(unsigned), buf->ctx->stream));
     return PPO_OK;
 }
 

@@ -83,6 +83,7 @@ struct ppo_batch {
     int* action = nullptr;     // [cap] 0-based
     float* old_prob = nullptr; // [cap]
     float* adv = nullptr;      // [cap]
+    const unsigned* feat_bound = nullptr;   // device word: bit pattern of an upper bound of |feat| (the buffer's abs-max), or nullptr
 };
 
 struct ppo_buf {
@@ -104,6 +105,7 @@ struct ppo_buf {
     int normalize = 0;
     double norm_eps = 1e-8;
     float* d_norm = nullptr;     // 2 floats: mean, 1/(std+eps)
+    unsigned* d_feat_absmax = nullptr;   // bit pattern of max |feat| over everything appended since the last clear
     double* d_tile_stats = nullptr; // per scan tile {sum, sumsq}
     int64_t n_tiles_stats = 0;
     bool stats_valid = false;
@@ -192,10 +194,12 @@ int launch_convert_actions_in(ppo_ctx* ctx, const int64_t* a1, int* a0, int64_t 
 int launch_convert_actions_out(ppo_ctx* ctx, const int* a0, int64_t* a1, int64_t n);
 int launch_linear_index_in(ppo_ctx* ctx, const int64_t* lin1, int* a0, int64_t n, int A, int* d_bad);
 int launch_i64_to_f32(ppo_ctx* ctx, const int64_t* src, float* dst, int64_t n);
-int launch_narrow_to_f32(ppo_ctx* ctx, const void* src, int elem_bytes /* 1: int8, 2: int16 */, float* dst, int64_t n);
+int launch_narrow_to_f32(ppo_ctx* ctx, const void* src, int elem_bytes /* 1: int8, 2: int16 */, float* dst, int64_t n,
+                         unsigned* absmax_out = nullptr /* optional: atomicMax of the bit pattern of max |value| */);
 int launch_normalize_bool(ppo_ctx* ctx, uint8_t* t, int64_t n);
 int launch_step_advance(ppo_ctx* ctx, int* d_step);
 int launch_mask_from_bits(ppo_ctx* ctx, const uint64_t* bits, float* mask, int64_t n);
+int launch_absmax_f32(ppo_ctx* ctx, const float* x, int64_t n, unsigned* out);
 
 // loss.cu (K6)
 int64_t loss_num_blocks(int64_t nb, int A);
@@ -203,7 +207,8 @@ int launch_loss(ppo_ctx* ctx, const float* logits, const float* mask, const int*
                 const float* old_prob, const float* adv, int64_t nb, int A, double epsilon,
                 double entropy_weight, double inv_nb_global, float* dlogits, double* partials,
                 double* loss_out2 /* {ppoloss, entropyloss unweighted} */, float* probs_out,
-                const int* step = nullptr /* optional device scalar: write to loss_out2 + 2 * (*step) */);
+                const int* step = nullptr /* optional device scalar: write to loss_out2 + 2 * (*step) */,
+                unsigned* dl_absmax = nullptr /* optional: atomicMax of the bit pattern of max |dlogits| */);
 
 int launch_sample_actions(ppo_ctx* ctx, const float* probs, int64_t nb, int A, uint64_t seed, int64_t* action1,
                           float* prob_out);

@@ -35,6 +35,16 @@ __device__ __forceinline__ void warp_copy_vec4(const float4* __restrict__ s, flo
     for (; i < nvec; i += 32) d[i] = __ldcs(s + i);
 }
 
+// the per-sample scalars of a record, by three lanes of the warp that copies it (no second launch)
+__device__ __forceinline__ void gather_record_scalars(const GatherArgs& a, int64_t rec, int64_t src, int lane) {
+    if (lane == 0 && a.action_out) a.action_out[rec] = a.action[src];
+    if (lane == 1 && a.prob_out) a.prob_out[rec] = a.old_prob[src];
+    if (lane == 2 && a.adv_out) {
+        const float r = a.ret[src];
+        a.adv_out[rec] = (a.norm != nullptr) ? (r - a.norm[0]) * a.norm[1] : r;
+    }
+}
+
 __global__ void __launch_bounds__(256)
 gather_rows_vec_kernel(GatherArgs a) {
     if (a.step != nullptr) a.index += (int64_t)(*a.step) * a.step_stride;   // minibatch number lives on the device (CUDA graph replay)
@@ -47,6 +57,7 @@ gather_rows_vec_kernel(GatherArgs a) {
                           reinterpret_cast<float4*>(a.feat_out + rec * a.feat_elems), fvec, lane);
         warp_copy_vec4<2>(reinterpret_cast<const float4*>(a.mask + src * a.mask_elems),
                           reinterpret_cast<float4*>(a.mask_out + rec * a.mask_elems), mvec, lane);
+        gather_record_scalars(a, rec, src, lane);
     }
 }
 
@@ -63,6 +74,7 @@ gather_rows_scalar_kernel(GatherArgs a) {
         const float* ms = a.mask + src * a.mask_elems;
         float* md = a.mask_out + rec * a.mask_elems;
         for (int i = lane; i < a.mask_elems; i += 32) md[i] = ms[i];
+        gather_record_scalars(a, rec, src, lane);
     }
 }
 
@@ -244,9 +256,28 @@ i64_to_f32_kernel(const int64_t* __restrict__ s, float* __restrict__ d, int64_t 
 }
 
 // narrow integer features -> Float32 (exact), 16 elements per thread: 16 / 32 bytes in, 64 bytes out
+// block-wide max of a non-negative float -> atomicMax on its bit pattern (order-independent, deterministic)
+__device__ __forceinline__ void block_absmax_to(float m, unsigned* out) {
+    if (out == nullptr) return;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, d));
+    if ((threadIdx.x & 31) == 0 && m > 0.0f) atomicMax(out, __float_as_uint(m));
+}
+
+// max |x| of a float array (the rollout buffer keeps the abs-max of its features up to date at every append, so that the
+// fp16-split engine has a bound for a minibatch's features without a pass over them)
+__global__ void __launch_bounds__(256)
+absmax_f32_kernel(const float* __restrict__ x, int64_t n, unsigned* out) {
+    float m = 0.0f;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        m = fmaxf(m, fabsf(__ldg(x + i)));
+    block_absmax_to(m, out);
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256)
-narrow_to_f32_kernel(const T* __restrict__ s, float* __restrict__ d, int64_t n) {
+narrow_to_f32_kernel(const T* __restrict__ s, float* __restrict__ d, int64_t n, unsigned* absmax_out) {
+    float amax = 0.0f;
     const int64_t n16 = n >> 4;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (int64_t)gridDim.x * blockDim.x) {
         T v[16];
@@ -259,9 +290,12 @@ narrow_to_f32_kernel(const T* __restrict__ s, float* __restrict__ d, int64_t n) 
 #pragma unroll
         for (int q = 0; q < 4; ++q)
             reinterpret_cast<float4*>(d)[4 * i + q] = make_float4((float)v[4 * q], (float)v[4 * q + 1], (float)v[4 * q + 2], (float)v[4 * q + 3]);
+#pragma unroll
+        for (int q = 0; q < 16; ++q) amax = fmaxf(amax, fabsf((float)v[q]));
     }
     const int64_t tail = (n16 << 4) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (blockIdx.x == 0 && tail < n) d[tail] = (float)s[tail];      // < 16 leftover elements
+    if (blockIdx.x == 0 && tail < n) { d[tail] = (float)s[tail]; amax = fmaxf(amax, fabsf((float)s[tail])); }      // < 16 leftover elements
+    block_absmax_to(amax, absmax_out);
 }
 
 // action mask from one bit per action (1 = allowed -> 0.0f, 0 = masked -> -Inf32): bit i of the stream is bit (i & 63)
@@ -275,9 +309,13 @@ mask_from_bits_kernel(const uint64_t* __restrict__ bits, float* __restrict__ mas
 // element-wise variant for a destination that is not 16-byte aligned (an append at an odd element offset)
 template <typename T>
 __global__ void __launch_bounds__(256)
-narrow_to_f32_scalar_kernel(const T* __restrict__ s, float* __restrict__ d, int64_t n) {
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+narrow_to_f32_scalar_kernel(const T* __restrict__ s, float* __restrict__ d, int64_t n, unsigned* absmax_out) {
+    float amax = 0.0f;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         d[i] = (float)s[i];
+        amax = fmaxf(amax, fabsf((float)s[i]));
+    }
+    block_absmax_to(amax, absmax_out);
 }
 
 inline unsigned grid_for(ppo_ctx* ctx, int64_t n, int per_block, int waves = 8) {
@@ -293,6 +331,7 @@ int launch_gather(ppo_ctx* ctx, const GatherArgs& a, int variant) {
     const bool vec_ok = (a.feat_elems % 4 == 0) && (a.mask_elems % 4 == 0) &&
                         ((uintptr_t)a.feat % 16 == 0) && ((uintptr_t)a.mask % 16 == 0) &&
                         ((uintptr_t)a.feat_out % 16 == 0) && ((uintptr_t)a.mask_out % 16 == 0);
+    bool scalars_done = false;
     if (a.feat_out != nullptr) {
         if (variant == 1 && vec_ok) {
             const int rec = (a.feat_elems + a.mask_elems) * 4;
@@ -313,13 +352,15 @@ int launch_gather(ppo_ctx* ctx, const GatherArgs& a, int variant) {
         } else if (vec_ok) {
             // 8 warps per block; enough blocks for ~2 waves at 8 blocks/SM
             gather_rows_vec_kernel<<<grid_for(ctx, a.count, 8, 16), 256, 0, ctx->stream>>>(a);
+            scalars_done = true;
         } else {
             gather_rows_scalar_kernel<<<grid_for(ctx, a.count, 8, 16), 256, 0, ctx->stream>>>(a);
+            scalars_done = true;
         }
         ctx->launches += 1;
         PPO_CUDA(cudaGetLastError());
     }
-    if (a.action_out || a.prob_out || a.adv_out) {
+    if (!scalars_done && (a.action_out || a.prob_out || a.adv_out)) {
         gather_scalars_kernel<<<grid_for(ctx, a.count, 256), 256, 0, ctx->stream>>>(a);
         ctx->launches += 1;
         PPO_CUDA(cudaGetLastError());
@@ -390,16 +431,24 @@ int launch_mask_from_bits(ppo_ctx* ctx, const uint64_t* bits, float* mask, int64
     return PPO_OK;
 }
 
-int launch_narrow_to_f32(ppo_ctx* ctx, const void* src, int elem_bytes, float* dst, int64_t n) {
+int launch_absmax_f32(ppo_ctx* ctx, const float* x, int64_t n, unsigned* out) {
+    if (n <= 0) return PPO_OK;
+    absmax_f32_kernel<<<grid_for(ctx, n, 1024, 8), 256, 0, ctx->stream>>>(x, n, out);
+    ctx->launches += 1;
+    PPO_CUDA(cudaGetLastError());
+    return PPO_OK;
+}
+
+int launch_narrow_to_f32(ppo_ctx* ctx, const void* src, int elem_bytes, float* dst, int64_t n, unsigned* absmax_out) {
     if (n <= 0) return PPO_OK;
     if (((uintptr_t)src % 16 == 0) && ((uintptr_t)dst % 16 == 0)) {
         const unsigned grid = grid_for(ctx, n / 16 + 1, 256, 16);
-        if (elem_bytes == 1) narrow_to_f32_kernel<int8_t><<<grid, 256, 0, ctx->stream>>>((const int8_t*)src, dst, n);
-        else narrow_to_f32_kernel<int16_t><<<grid, 256, 0, ctx->stream>>>((const int16_t*)src, dst, n);
+        if (elem_bytes == 1) narrow_to_f32_kernel<int8_t><<<grid, 256, 0, ctx->stream>>>((const int8_t*)src, dst, n, absmax_out);
+        else narrow_to_f32_kernel<int16_t><<<grid, 256, 0, ctx->stream>>>((const int16_t*)src, dst, n, absmax_out);
     } else {
         const unsigned grid = grid_for(ctx, n, 256, 16);
-        if (elem_bytes == 1) narrow_to_f32_scalar_kernel<int8_t><<<grid, 256, 0, ctx->stream>>>((const int8_t*)src, dst, n);
-        else narrow_to_f32_scalar_kernel<int16_t><<<grid, 256, 0, ctx->stream>>>((const int16_t*)src, dst, n);
+        if (elem_bytes == 1) narrow_to_f32_scalar_kernel<int8_t><<<grid, 256, 0, ctx->stream>>>((const int8_t*)src, dst, n, absmax_out);
+        else narrow_to_f32_scalar_kernel<int16_t><<<grid, 256, 0, ctx->stream>>>((const int16_t*)src, dst, n, absmax_out);
     }
     ctx->launches += 1;
     PPO_CUDA(cudaGetLastError());

@@ -706,29 +706,57 @@ __global__ void plan_w_kernel(int L, const unsigned* wstats, float* sc) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     for (int l = 0; l + 1 < L; ++l) write_scale(sc + 2 * sc_w(L, l), __uint_as_float(wstats[4 * l]));
 }
-// consumes (and clears) the abs-max of the minibatch features
-__global__ void plan_fwd_kernel(int L, float slope, unsigned* st_x0, const unsigned* wstats, float* sc) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    float B = __uint_as_float(*st_x0);
-    *st_x0 = 0u;
-    write_scale(sc + 2 * sc_act(0), B);
-    const float amp = fmaxf(1.0f, fabsf(slope));
+// Forward plan: scales of X0 and of every hidden activation from a bound of the input features and the weight statistics.
+// The bound is the minibatch's own abs-max (st_x0: consumed and cleared) or, when the rollout buffer supplies one, the
+// abs-max of everything the buffer holds (feat_bound: read only).  Also clears the abs-max word of dlogits, which the
+// loss kernel of this minibatch accumulates into (plan_bwd reads it, nobody clears it after).
+struct PlanFwd {
+    int L;                       // 0: nothing to do
+    float slope;
+    unsigned* st_x0;
+    const unsigned* feat_bound;
+    const unsigned* wstats;
+    float* sc;
+    unsigned* st_dl;
+};
+__device__ __forceinline__ void plan_fwd_body(const PlanFwd& pf) {
+    const int L = pf.L;
+    float B;
+    if (pf.feat_bound != nullptr) B = __uint_as_float(__ldcg(pf.feat_bound));
+    else { B = __uint_as_float(*pf.st_x0); *pf.st_x0 = 0u; }
+    if (pf.st_dl != nullptr) *pf.st_dl = 0u;
+    write_scale(pf.sc + 2 * sc_act(0), B);
+    const float amp = fmaxf(1.0f, fabsf(pf.slope));
     for (int l = 0; l + 1 < L; ++l) {
-        B = (B * __uint_as_float(wstats[4 * l + 1]) + __uint_as_float(wstats[4 * l + 3])) * amp;
+        B = (B * __uint_as_float(pf.wstats[4 * l + 1]) + __uint_as_float(pf.wstats[4 * l + 3])) * amp;
         B *= 1.0009765625f;      // the bound itself is evaluated in fp32
-        write_scale(sc + 2 * sc_act(l + 1), B);
+        write_scale(pf.sc + 2 * sc_act(l + 1), B);
     }
 }
-// consumes (and clears) the abs-max of dlogits
+__global__ void plan_fwd_kernel(PlanFwd pf) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    plan_fwd_body(pf);
+}
+// Backward plan: G(dZ_{l-1}) = G(dZ_l) * max_k sum_n |W_l[k][n]| from the abs-max of dlogits (dZ_{L-1} = dlogits); `write`:
+// store the scales (one block does); returns the scale pair of dZ_{L-2}, the head's output
+__device__ __forceinline__ float2 plan_bwd_body(int L, float slope, const unsigned* st_dl, const unsigned* wstats, float* sc, bool write) {
+    float G = __uint_as_float(__ldcg(st_dl));
+    const float amp = fmaxf(1.0f, fabsf(slope));
+    float2 head = make_float2(1.0f, 1.0f);
+    for (int l = L - 1; l >= 1; --l) {      // dZ_{l-1} = (dZ_l W_l^T) .* act'
+        G = G * __uint_as_float(__ldcg(wstats + 4 * l + 2)) * amp * 1.0009765625f;
+        float tmp[2];
+        write_scale(tmp, G);
+        if (write) { sc[2 * sc_dz(L, l - 1)] = tmp[0]; sc[2 * sc_dz(L, l - 1) + 1] = tmp[1]; }
+        if (l == L - 1) head = make_float2(tmp[0], tmp[1]);
+    }
+    return head;
+}
+// stand-alone (the abs-max word came from absmax_kernel; consumed and cleared here)
 __global__ void plan_bwd_kernel(int L, float slope, unsigned* st_dl, const unsigned* wstats, float* sc) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    float G = __uint_as_float(*st_dl);
+    plan_bwd_body(L, slope, st_dl, wstats, sc, true);
     *st_dl = 0u;
-    const float amp = fmaxf(1.0f, fabsf(slope));
-    for (int l = L - 1; l >= 1; --l) {      // dZ_{l-1} = (dZ_l W_l^T) .* act'   (dZ_{L-1} = dlogits)
-        G = G * __uint_as_float(wstats[4 * l + 2]) * amp * 1.0009765625f;
-        write_scale(sc + 2 * sc_dz(L, l - 1), G);
-    }
 }
 __global__ void scale_from_stat_kernel(unsigned* st, float* sc) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
@@ -1265,9 +1293,10 @@ token_count_kernel(const float* __restrict__ mask, int64_t M, int apa, int* __re
 }
 __global__ void __launch_bounds__(TOK_THREADS)
 token_compact_kernel(const float* __restrict__ mask, int64_t M, int apa, const int* __restrict__ blk_counts,
-                     int* __restrict__ tok_of_row, int* __restrict__ rows_out) {
+                     int* __restrict__ tok_of_row, int* __restrict__ rows_out, const PlanFwd pf) {
     __shared__ int sm[32];
     __shared__ int wsum[32];
+    if (pf.L > 0 && blockIdx.x == 0 && threadIdx.x == 0) plan_fwd_body(pf);      // (one launch less than a plan kernel of its own)
     int before = 0;
     for (int i = threadIdx.x; i < (int)blockIdx.x; i += TOK_THREADS) before += blk_counts[i];
     before = block_sum_1024(before, sm);
@@ -1425,8 +1454,17 @@ __global__ void __launch_bounds__(256, 2)
 head_bwd16_kernel(const __half* __restrict__ H_hi, const __half* __restrict__ H_lo,
                   const float* __restrict__ dlogits, const float* __restrict__ W, __half* __restrict__ dH_hi, __half* __restrict__ dH_lo,
                   float* __restrict__ partial, int64_t M, int K, float slope, int64_t rows_per_cta, int need_dH,
-                  const float* sc_h, const float* sc_dh, const int* __restrict__ M_dev, const int* __restrict__ tok_of_row) {
+                  const float* sc_h, const float* sc_dh, const int* __restrict__ M_dev, const int* __restrict__ tok_of_row,
+                  int plan_L, const unsigned* __restrict__ plan_st_dl, const unsigned* __restrict__ plan_wstats, float* plan_sc) {
     extern __shared__ float red[];                     // [rpp][K*N + N + K]
+    // plan_L > 0: the backward plan (scales of every activation gradient from max |dlogits|, which the loss kernel left in
+    // plan_st_dl) is evaluated here by every CTA for itself -- a handful of multiplies -- and stored by CTA 0 for the
+    // kernels that follow, instead of an abs-max pass over dlogits and a one-thread plan kernel in front of this one
+    __shared__ float s_plan_scale;
+    if (plan_L > 0) {
+        if (threadIdx.x == 0) s_plan_scale = plan_bwd_body(plan_L, slope, plan_st_dl, plan_wstats, plan_sc, blockIdx.x == 0).x;
+        __syncthreads();
+    }
     const int64_t M_alloc = M;
     if (M_dev != nullptr) {      // token compaction: rows = active tokens, row r reads the dlogits of token tok_of_row[r]
         M = min((int64_t)__ldg(M_dev), M);
@@ -1439,7 +1477,7 @@ head_bwd16_kernel(const __half* __restrict__ H_hi, const __half* __restrict__ H_
     const bool active = rg < rpp;
     const int k = 4 * ct;
     const float inv_h = __ldg(sc_h + 1);
-    const float s_dh = need_dH ? __ldg(sc_dh) : 1.0f;
+    const float s_dh = need_dH ? (plan_L > 0 ? s_plan_scale : __ldg(sc_dh)) : 1.0f;
     float w[4][N], aw[4][N], ab[N], cs[4];
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
@@ -1859,7 +1897,8 @@ int head_fwd16(ppo_ctx* ctx, const __half* H_hi, const __half* H_lo, const float
 int head_bwd16(ppo_ctx* ctx, const __half* H_hi, const __half* H_lo, const float* dlogits, const float* W, __half* dH_hi,
                __half* dH_lo, float* dW, float* db, float* db_below, int64_t M, int K, int N, float slope, float* partial,
                size_t partial_bytes, const float* sc_h, const float* sc_dh, const int* M_dev = nullptr,
-               const int* tok_of_row = nullptr, FoldList* defer = nullptr) {
+               const int* tok_of_row = nullptr, FoldList* defer = nullptr, int plan_L = 0, const unsigned* plan_st_dl = nullptr,
+               const unsigned* plan_wstats = nullptr, float* plan_sc = nullptr) {
     PPO_REQUIRE(N >= 1 && N <= 4 && K % 4 == 0 && K >= 4 && K <= 1024, "f16 head_bwd: needs N <= 4, K %% 4 == 0, K <= 1024 (K=%d N=%d)", K, N);
     const int64_t ctas = head16_ctas(M, ctx->num_sms);
     const int64_t rows = ceil_div(M, ctas);
@@ -1869,10 +1908,10 @@ int head_bwd16(ppo_ctx* ctx, const __half* H_hi, const __half* H_lo, const float
     const int rpp = 256 / (K / 4);
     const size_t smem = (size_t)rpp * stride * sizeof(float);
     switch (N) {
-        case 1: head_bwd16_kernel<1><<<(unsigned)ctas, 256, smem, ctx->stream>>>(H_hi, H_lo, dlogits, W, dH_hi, dH_lo, partial, M, K, slope, rows, need_dH, sc_h, sc_dh, M_dev, tok_of_row); break;
-        case 2: head_bwd16_kernel<2><<<(unsigned)ctas, 256, smem, ctx->stream>>>(H_hi, H_lo, dlogits, W, dH_hi, dH_lo, partial, M, K, slope, rows, need_dH, sc_h, sc_dh, M_dev, tok_of_row); break;
-        case 3: head_bwd16_kernel<3><<<(unsigned)ctas, 256, smem, ctx->stream>>>(H_hi, H_lo, dlogits, W, dH_hi, dH_lo, partial, M, K, slope, rows, need_dH, sc_h, sc_dh, M_dev, tok_of_row); break;
-        default: head_bwd16_kernel<4><<<(unsigned)ctas, 256, smem, ctx->stream>>>(H_hi, H_lo, dlogits, W, dH_hi, dH_lo, partial, M, K, slope, rows, need_dH, sc_h, sc_dh, M_dev, tok_of_row); break;
+        case 1: head_bwd16_kernel<1><<<(unsigned)ctas, 256, smem, ctx->stream>>>(H_hi, H_lo, dlogits, W, dH_hi, dH_lo, partial, M, K, slope, rows, need_dH, sc_h, sc_dh, M_dev, tok_of_row, plan_L, plan_st_dl, plan_wstats, plan_sc); break;
+        case 2: head_bwd16_kernel<2><<<(unsigned)ctas, 256, smem, ctx->stream>>>(H_hi, H_lo, dlogits, W, dH_hi, dH_lo, partial, M, K, slope, rows, need_dH, sc_h, sc_dh, M_dev, tok_of_row, plan_L, plan_st_dl, plan_wstats, plan_sc); break;
+        case 3: head_bwd16_kernel<3><<<(unsigned)ctas, 256, smem, ctx->stream>>>(H_hi, H_lo, dlogits, W, dH_hi, dH_lo, partial, M, K, slope, rows, need_dH, sc_h, sc_dh, M_dev, tok_of_row, plan_L, plan_st_dl, plan_wstats, plan_sc); break;
+        default: head_bwd16_kernel<4><<<(unsigned)ctas, 256, smem, ctx->stream>>>(H_hi, H_lo, dlogits, W, dH_hi, dH_lo, partial, M, K, slope, rows, need_dH, sc_h, sc_dh, M_dev, tok_of_row, plan_L, plan_st_dl, plan_wstats, plan_sc); break;
     }
     ctx->launches += 1;
     PPO_CUDA(cudaGetLastError());
@@ -2036,24 +2075,28 @@ int f16_adam_refresh(ppo_policy* p, ppo_opt* opt, const P2PView* xv, int* d_step
 
 int f16_refresh_weights(ppo_policy* p) { return f16_adam_refresh(p, nullptr, nullptr, nullptr); }
 
-int f16_forward(ppo_policy* p, const float* X, int64_t M, const float* mask) {
+int f16_forward(ppo_policy* p, const float* X, int64_t M, const float* mask, const unsigned* feat_bound) {
     F16State* st = state(p);
     PPO_REQUIRE(st != nullptr, "fp16-split engine not prepared");
     ppo_ctx* ctx = p->ctx;
     const int L = p->L;
     PPO_TRY(ensure_f16_workspace(p, p->ws_tokens > M ? p->ws_tokens : M));
-    PPO_TRY(launch_absmax(ctx, X, M * p->dims[0], st->st + 0));      // over all tokens: a bound is all the plan needs
-    plan_fwd_kernel<<<1, 32, 0, ctx->stream>>>(L, p->slope, st->st + 0, st->st + 2, st->sc);
-    ctx->launches += 1;
+    // a bound of |X| is all the plan needs: the rollout buffer's running abs-max when it supplies one, else a pass over X
+    if (feat_bound == nullptr) PPO_TRY(launch_absmax(ctx, X, M * p->dims[0], st->st + 0));
+    PlanFwd pf{L, p->slope, st->st + 0, feat_bound, st->st + 2, st->sc, st->st + 1};
     // token compaction (mask: the minibatch's [rows][nhe * apa] action mask, or nullptr = run every token)
     st->compact = mask != nullptr && p->compact_tokens != 0 && M >= 1;
+    if (!st->compact) {       // (compacted: token_compact_kernel evaluates the plan)
+        plan_fwd_kernel<<<1, 32, 0, ctx->stream>>>(pf);
+        ctx->launches += 1;
+    }
     const int* M_dev = st->compact ? st->d_rows : nullptr;
     const int* tok = st->compact ? st->tok_of_row : nullptr;
     if (st->compact) {
         const int apa = p->dims[L];
         const unsigned nblk = (unsigned)ceil_div(M, TOK_PER_BLOCK);
         token_count_kernel<<<nblk, TOK_THREADS, 0, ctx->stream>>>(mask, M, apa, st->blk_counts);
-        token_compact_kernel<<<nblk, TOK_THREADS, 0, ctx->stream>>>(mask, M, apa, st->blk_counts, st->tok_of_row, st->d_rows);
+        token_compact_kernel<<<nblk, TOK_THREADS, 0, ctx->stream>>>(mask, M, apa, st->blk_counts, st->tok_of_row, st->d_rows, pf);
         const int K8 = p->dims[0] / 8;
         const int64_t blocks = std::max<int64_t>(1, std::min<int64_t>(ceil_div(M * K8, 256), (int64_t)ctx->num_sms * 16));
         split16_rows_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(X, tok, M_dev, K8, st->x_hi, st->x_lo, st->sc + 2 * sc_act(0), M);
@@ -2079,7 +2122,7 @@ int f16_forward(ppo_policy* p, const float* X, int64_t M, const float* mask) {
                       p->act[L], M, p->dims[L - 1], p->dims[L], st->sc + 2 * sc_act(L - 1), M_dev, tok);
 }
 
-int f16_backward(ppo_policy* p, int64_t M) {
+int f16_backward(ppo_policy* p, int64_t M, bool dl_stat_ready) {
     F16State* st = state(p);
     PPO_REQUIRE(st != nullptr, "fp16-split engine not prepared");
     ppo_ctx* ctx = p->ctx;
@@ -2087,9 +2130,13 @@ int f16_backward(ppo_policy* p, int64_t M) {
     PPO_REQUIRE(M <= st->tokens, "fp16-split engine: backward without a forward of the same minibatch");
     const int* M_dev = st->compact ? st->d_rows : nullptr;
     const int* tok = st->compact ? st->tok_of_row : nullptr;
-    PPO_TRY(launch_absmax(ctx, p->dlogits, M * p->dims[L], st->st + 1));
-    plan_bwd_kernel<<<1, 32, 0, ctx->stream>>>(L, p->slope, st->st + 1, st->st + 2, st->sc);
-    ctx->launches += 1;
+    // scales of the activation gradients: from max |dlogits|.  dl_stat_ready: the loss kernel already left it in st[1]
+    // and the head kernel evaluates the plan itself; otherwise an abs-max pass and the plan kernel run first
+    if (!dl_stat_ready) {
+        PPO_TRY(launch_absmax(ctx, p->dlogits, M * p->dims[L], st->st + 1));
+        plan_bwd_kernel<<<1, 32, 0, ctx->stream>>>(L, p->slope, st->st + 1, st->st + 2, st->sc);
+        ctx->launches += 1;
+    }
     int pp = 0;
     // The reductions of the partials (split-K, column sums, head) are deferred to two launches at the end of the pass --
     // except under the per-layer overlapped NCCL all-reduce, which wants every layer's gradient as early as possible.
@@ -2110,7 +2157,8 @@ int f16_backward(ppo_policy* p, int64_t M) {
         PPO_TRY(head_bwd16(ctx, st->act_hi[L - 1], st->act_lo[L - 1], p->dlogits, p->params + p->w_off[L - 1], st->dz_hi[pp],
                            st->dz_lo[pp], p->grads + p->w_off[L - 1], p->grads + p->b_off[L - 1], p->grads + p->b_off[L - 2], M,
                            p->dims[L - 1], p->dims[L], p->slope, part, st->partial_bytes - (size_t)((char*)part - arena),
-                           st->sc + 2 * sc_act(L - 1), st->sc + 2 * sc_dz(L, L - 2), M_dev, tok, defer));
+                           st->sc + 2 * sc_act(L - 1), st->sc + 2 * sc_dz(L, L - 2), M_dev, tok, defer,
+                           dl_stat_ready ? L : 0, st->st + 1, st->st + 2, st->sc));
     }
     // data parallelism: a layer's slice of the flat gradient vector (dW_l, db_l: contiguous in Flux.params order) is
     // all-reduced on the communication stream as soon as it is complete, while the layers below still compute
@@ -2168,6 +2216,12 @@ int f16_read_gates(ppo_policy* p, int l, int64_t M, uint8_t* d_out) {
     }
     PPO_CUDA(cudaGetLastError());
     return PPO_OK;
+}
+
+// the device word the loss kernel accumulates max |dlogits| into (bit pattern of a non-negative float)
+unsigned* f16_dlogits_stat(ppo_policy* p) {
+    F16State* st = state(p);
+    return st != nullptr ? st->st + 1 : nullptr;
 }
 
 // active tokens of the last forward pass (-1: it ran every token)

@@ -16,9 +16,13 @@ int f16_adam_refresh(ppo_policy* p, ppo_opt* opt, const P2PView* xv, int* d_step
 // whole-MLP forward: X fp32 [M][dims[0]] -> p->act[L] (fp32 logits); hidden activations stay fp16 hi/lo pairs.
 // mask (optional): the minibatch's action mask [M * apa]; with p->compact_tokens the MLP then runs only on the tokens
 // that have at least one unmasked action (the logits of the others never reach the loss: softmax(-Inf) = 0)
-int f16_forward(ppo_policy* p, const float* X, int64_t M, const float* mask);
+// feat_bound (optional): device word holding the bit pattern of an upper bound of |X| (the rollout buffer's abs-max)
+int f16_forward(ppo_policy* p, const float* X, int64_t M, const float* mask, const unsigned* feat_bound = nullptr);
+// where the loss kernel leaves max |dlogits| for the backward pass (launch_loss's dl_absmax)
+unsigned* f16_dlogits_stat(ppo_policy* p);
 // whole-MLP backward from p->dlogits -> p->grads
-int f16_backward(ppo_policy* p, int64_t M);
+// dl_stat_ready: f16_dlogits_stat() already holds max |dlogits| of this minibatch (no abs-max pass, plan inside the head kernel)
+int f16_backward(ppo_policy* p, int64_t M, bool dl_stat_ready = false);
 // the leakyrelu' gates of hidden activation l (1..L-1) as the backward pass of the last minibatch applies them
 // (tokens the compacted MLP skipped: PPO_GATE_SKIPPED)
 int f16_read_gates(ppo_policy* p, int l, int64_t M, uint8_t* d_out);

@@ -53,7 +53,17 @@ struct LossArgs {
     float inv_nb;                      // 1 / nb_global
     float smooth_over_A;               // fl32(1f-8 / A)
     float* dlogits; float* probs_out; double* partials;
+    unsigned* dl_absmax;               // optional: max |dlogits| as the bit pattern of a non-negative float (atomicMax)
 };
+
+// max |dlogits| of the block -> atomicMax (order-independent, deterministic): the fp16-split engine derives the scale of
+// the gradient operands from it, so the separate abs-max pass over dlogits is not needed
+__device__ __forceinline__ void block_absmax_store(float m, unsigned* out) {
+    if (out == nullptr) return;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, d));
+    if ((threadIdx.x & 31) == 0 && m > 0.0f) atomicMax(out, __float_as_uint(m));
+}
 
 __device__ __forceinline__ void block_reduce_store(double a, double b, double* partials) {
     __shared__ double sa[LOSS_THREADS / 32], sb[LOSS_THREADS / 32];
@@ -93,6 +103,7 @@ loss_vec_kernel(LossArgs a) {
     const unsigned lane = threadIdx.x & 31u;
     const unsigned group_base = lane - (lane % G);
     double acc_ppo = 0.0, acc_ent = 0.0;
+    float amax = 0.0f;
 
     for (int64_t s0 = (int64_t)blockIdx.x * SPB; s0 < a.nb; s0 += (int64_t)gridDim.x * SPB) {
         const int64_t b = s0 + gi;
@@ -161,9 +172,12 @@ loss_vec_kernel(LossArgs a) {
             if (a.dlogits != nullptr) {
                 float4* dp = reinterpret_cast<float4*>(a.dlogits + b * a.A);
 #pragma unroll
-                for (int v = 0; v < V; ++v)
-                    dp[gl + G * v] = make_float4(z[v][0] * (g[v][0] - dot), z[v][1] * (g[v][1] - dot),
-                                                 z[v][2] * (g[v][2] - dot), z[v][3] * (g[v][3] - dot));
+                for (int v = 0; v < V; ++v) {
+                    const float4 d4 = make_float4(z[v][0] * (g[v][0] - dot), z[v][1] * (g[v][1] - dot),
+                                                  z[v][2] * (g[v][2] - dot), z[v][3] * (g[v][3] - dot));
+                    dp[gl + G * v] = d4;
+                    amax = fmaxf(fmaxf(amax, fmaxf(fabsf(d4.x), fabsf(d4.y))), fmaxf(fabsf(d4.z), fabsf(d4.w)));
+                }
             }
             if (a.probs_out != nullptr) {
                 float4* pp = reinterpret_cast<float4*>(a.probs_out + b * a.A);
@@ -173,6 +187,7 @@ loss_vec_kernel(LossArgs a) {
             if (gl == 0) { acc_ppo += mn; acc_ent += (double)(-ent); }
         }
     }
+    block_absmax_store(amax, a.dl_absmax);
     block_reduce_store(acc_ppo, acc_ent, a.partials);
 }
 
@@ -182,6 +197,7 @@ loss_generic_kernel(LossArgs a) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     constexpr int WPB = LOSS_THREADS / 32;
     double acc_ppo = 0.0, acc_ent = 0.0;
+    float amax = 0.0f;
     for (int64_t b = (int64_t)blockIdx.x * WPB + warp; b < a.nb; b += (int64_t)gridDim.x * WPB) {
         const float* zp = a.logits + b * a.A;
         const float* mp = a.mask + b * a.A;
@@ -214,11 +230,12 @@ loss_generic_kernel(LossArgs a) {
             const float ps = p + a.smooth_over_A;
             float g = a.c_ent * (logf(ps) + 1.0f);
             if (i == act) g -= coef;
-            if (a.dlogits != nullptr) a.dlogits[b * a.A + i] = p * (g - dot);
+            if (a.dlogits != nullptr) { const float dz = p * (g - dot); a.dlogits[b * a.A + i] = dz; amax = fmaxf(amax, fabsf(dz)); }
             if (a.probs_out != nullptr) a.probs_out[b * a.A + i] = p;
         }
         if (lane == 0) { acc_ppo += mn; acc_ent += (double)(-ent); }
     }
+    block_absmax_store(amax, a.dl_absmax);
     block_reduce_store(acc_ppo, acc_ent, a.partials);
 }
 
@@ -266,7 +283,8 @@ int64_t loss_num_blocks(int64_t nb, int A) {
 
 int launch_loss(ppo_ctx* ctx, const float* logits, const float* mask, const int* action, const float* old_prob,
                 const float* adv, int64_t nb, int A, double epsilon, double entropy_weight, double inv_nb_global,
-                float* dlogits, double* partials, double* loss_out2, float* probs_out, const int* step) {
+                float* dlogits, double* partials, double* loss_out2, float* probs_out, const int* step,
+                unsigned* dl_absmax) {
     PPO_REQUIRE(nb >= 1 && A >= 1, "loss: nb=%lld A=%d", (long long)nb, A);
     LossArgs a;
     a.logits = logits; a.mask = mask; a.action = action; a.old_prob = old_prob; a.adv = adv;
@@ -275,6 +293,7 @@ int launch_loss(ppo_ctx* ctx, const float* logits, const float* mask, const int*
     a.c_ent = (float)entropy_weight * (float)inv_nb_global;
     a.smooth_over_A = 1e-8f / (float)A;
     a.dlogits = dlogits; a.probs_out = probs_out; a.partials = partials;
+    a.dl_absmax = dlogits != nullptr ? dl_absmax : nullptr;
     const int64_t blocks = loss_num_blocks(nb, A);
     Cfg c;
     const bool aligned = ((uintptr_t)logits % 16 == 0) && ((uintptr_t)mask % 16 == 0) &&
