@@ -271,8 +271,14 @@ extern "C" int ppo_bench_kernel(ppo_ctx* ctx, const char* which, int64_t n, int 
         PPO_TRY(sc.alloc(&Xh, (size_t)M * K + 128)); PPO_TRY(sc.alloc(&Xl, (size_t)M * K + 128));
         PPO_TRY(sc.alloc(&Wh, (size_t)K * N)); PPO_TRY(sc.alloc(&Wl, (size_t)K * N));
         PPO_TRY(sc.alloc(&WTh, (size_t)K * N)); PPO_TRY(sc.alloc(&WTl, (size_t)K * N));
-        PPO_TRY(sc.alloc(&Yh, (size_t)M * N + 128)); PPO_TRY(sc.alloc(&Yl, (size_t)M * N + 128));
-        PPO_TRY(sc.alloc(&dXh, (size_t)M * K + 128)); PPO_TRY(sc.alloc(&dXl, (size_t)M * K + 128));
+        // output pairs as the engine allocates them: hi and lo planes of one allocation, the lo plane a whole number of
+        // rows behind (one 3-D TMA store box covers both)
+        {
+            const size_t py = (size_t)round_up((int64_t)((size_t)M * N + 128) * 2, (int64_t)N * 2 * 128) / 2;
+            const size_t px = (size_t)round_up((int64_t)((size_t)M * K + 128) * 2, (int64_t)K * 2 * 128) / 2;
+            PPO_TRY(sc.alloc(&Yh, 2 * py)); Yl = Yh + py;
+            PPO_TRY(sc.alloc(&dXh, 2 * px)); dXl = dXh + px;
+        }
         PPO_TRY(sc.alloc(&dW, (size_t)K * N)); PPO_TRY(sc.alloc(&db, (size_t)std::max(K, N)));
         PPO_TRY(sc.alloc(&sc_, 16)); PPO_TRY(sc.alloc(&st, 4)); PPO_TRY(sc.alloc(&lg, (size_t)M * 4));
         const size_t pb = std::max(f16_test_partial_bytes(ctx, M, K, N), f16_test_head_partial_bytes(M, K, N <= 4 ? N : 4));

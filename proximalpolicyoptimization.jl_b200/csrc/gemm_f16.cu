@@ -127,6 +127,8 @@ struct KK16Params {
     const float* sc_a;       // {scale, 1/scale} of the A operand
     const float* sc_b;
     const float* sc_c;       // of the output
+    int store3d;             // the output's hi and lo planes are stored by ONE 3-D TMA box per 16-column group (tmC_hi is the
+                             // 3-D map {16 cols, 32 rows, 2 planes}); 0: two 2-D stores
     int chunk_kb;            // k-blocks per TMEM accumulation chain
     // The tensor core adds each MMA result into its fp32 accumulator with round-toward-zero: every add loses on average
     // ~0.72 * 2^-24 of the running sum, always towards zero, so a chain of n MMAs comes out short by ~ n/2 of that (the
@@ -339,8 +341,14 @@ f16_gemm_kk_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
         uint4* st_hi = reinterpret_cast<uint4*>(staging + (warp - 2) * 2048);
         uint4* st_lo = st_hi + 32 * 2;                 // + 1024 B
         const int swz = (lane >> 2) & 1;               // SWIZZLE_32B: 16-byte chunk c of row r goes to chunk c ^ ((r >> 2) & 1)
-        const float unscale = __ldg(p.sc_a + 1) * __ldg(p.sc_b + 1);
+        // every scale is a power of two, so folding them into one another changes no rounding: the accumulator is folded
+        // straight into the OUTPUT's scaled domain (x 2^-(eA + eB) x 2^eC), the bias joins it pre-scaled
         const float cscale = __ldg(p.sc_c);
+        const float uc = __ldg(p.sc_a + 1) * __ldg(p.sc_b + 1) * cscale;
+        const float inv_cscale = __ldg(p.sc_c + 1);
+        // leakyrelu(x) = max(x, slope x) for 0 <= slope <= 1 (one FMNMX instead of a compare-select); act = 0: identity
+        const float slope_eff = p.act ? p.slope : 1.0f;
+        const bool slope_unit = slope_eff >= 0.0f && slope_eff <= 1.0f;
         uint32_t cc = 0;
         for (int tile = unit0; tile < num_tiles; tile += unit_step) {
             const int mt = m_tile_of(tile);
@@ -348,8 +356,29 @@ f16_gemm_kk_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
             const int row = m0 + row_in_tile;
             const bool mt_valid = mt < tiles_m;
             float s[CPT];
+            if (p.epi == F_EPI_FWD && p.bias != nullptr) {
+                // the accumulation starts from the (pre-scaled) bias, fetched before the contraction finishes
 #pragma unroll
-            for (int j = 0; j < CPT; ++j) s[j] = 0.0f;
+                for (int g = 0; g < CPT / 32; ++g) {
+                    const int col0 = n0 + cq * CPT + g * 32;
+                    if (col0 + 32 <= p.N) {
+#pragma unroll
+                        for (int j4 = 0; j4 < 8; ++j4) {
+                            const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0) + j4);
+                            s[g * 32 + 4 * j4 + 0] = b4.x * cscale; s[g * 32 + 4 * j4 + 1] = b4.y * cscale;
+                            s[g * 32 + 4 * j4 + 2] = b4.z * cscale; s[g * 32 + 4 * j4 + 3] = b4.w * cscale;
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) s[g * 32 + j] = (col0 + j < p.N) ? __ldg(p.bias + col0 + j) * cscale : 0.0f;
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < CPT; ++j) s[j] = 0.0f;
+            }
+            // dgrad: rows beyond the data contribute zeros (also to the column sums)
+            const float row_uc = (p.epi == F_EPI_DGRAD && row >= M_rows) ? 0.0f : uc;
             // dgrad: this thread's gate bits (one word per 32 columns), fetched before the contraction finishes
             uint32_t gbits[CPT / 32];
             if (p.epi == F_EPI_DGRAD) {
@@ -365,7 +394,7 @@ f16_gemm_kk_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
                 tc_fence_after();
                 const int kb_in_chunk = (ch + 1) * p.chunk_kb <= p.k_blocks ? p.chunk_kb : p.k_blocks - ch * p.chunk_kb;
                 drain_chunk16_narrow<CPT>(tmem_base + (uint32_t)(acc * BN + cq * CPT) + ((uint32_t)(q * 32) << 16), s,
-                                          1.0f + p.rz_comp * (float)(3 * (F_BK / 16) * kb_in_chunk));
+                                          (1.0f + p.rz_comp * (float)(3 * (F_BK / 16) * kb_in_chunk)) * row_uc);
                 tc_fence_before();
                 if (TWO) {
                     __syncwarp();
@@ -380,36 +409,30 @@ f16_gemm_kk_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
                 const int col0 = n0 + cq * CPT + g * 32;
                 float* v = s + g * 32;
                 if (p.epi == F_EPI_FWD) {
+                    // v = scaled pre-activation (bias included): sign bit, leakyrelu
                     uint32_t w = 0u;
-                    const bool full = (p.bias != nullptr) && (col0 + 32 <= p.N);
+                    if (slope_unit) {
 #pragma unroll
-                    for (int j4 = 0; j4 < 8; ++j4) {
-                        float4 b4 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-                        if (full) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0) + j4);
-                        else if (p.bias != nullptr) {
-                            const int c = col0 + 4 * j4;
-                            if (c < p.N) b4.x = __ldg(p.bias + c);
-                            if (c + 1 < p.N) b4.y = __ldg(p.bias + c + 1);
-                            if (c + 2 < p.N) b4.z = __ldg(p.bias + c + 2);
-                            if (c + 3 < p.N) b4.w = __ldg(p.bias + c + 3);
+                        for (int j = 0; j < 32; ++j) {
+                            const float x = v[j];
+                            asm("{\n.reg .pred p;\nsetp.gt.f32 p, %1, 0f00000000;\n@p or.b32 %0, %0, %2;\n}" : "+r"(w) : "f"(x), "r"(1u << j));
+                            v[j] = fmaxf(x, slope_eff * x);
                         }
-                        const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+                    } else {
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            const int j = 4 * j4 + i;
-                            const float x = fmaf(v[j], unscale, bb[i]);
+                        for (int j = 0; j < 32; ++j) {
+                            const float x = v[j];
                             const bool pos = x > 0.0f;
                             w |= (pos ? 1u : 0u) << j;
-                            v[j] = (p.act && !pos) ? p.slope * x : x;
+                            v[j] = pos ? x : slope_eff * x;
                         }
                     }
                     if (p.signs_out != nullptr && col0 < p.N && mt_valid) p.signs_out[sign_index(row, col0 >> 5, p.N >> 5)] = w;
                 } else {
-                    const float inb = (row < M_rows) ? unscale : 0.0f;     // rows beyond the data: keep them out of the column sums
-                    const float ins = inb * p.slope;
+                    // v = scaled dY W^T: the gate picks 1 or the slope
                     const uint32_t w = gbits[g];
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] *= ((w >> j) & 1u) ? inb : ins;
+                    for (int j = 0; j < 32; ++j) v[j] = ((w >> j) & 1u) ? v[j] : v[j] * p.slope;
                 }
 #pragma unroll
                 for (int hh = 0; hh < 2; ++hh) {
@@ -419,16 +442,29 @@ f16_gemm_kk_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
                         float cs; int cidx;
                         colsum16(vv, lane, cs, cidx);
                         if ((lane & 1) == 0 && col0 + 16 * hh + cidx < p.N && mt_valid)
-                            p.colsum_partial[((size_t)mt * 4 + q) * p.N + col0 + 16 * hh + cidx] = cs;
+                            p.colsum_partial[((size_t)mt * 4 + q) * p.N + col0 + 16 * hh + cidx] = cs * inv_cscale;
                     }
                     uint4 h[2], l[2];
 #pragma unroll
                     for (int j8 = 0; j8 < 2; ++j8) {
-                        f16_split2(vv[8 * j8 + 0] * cscale, vv[8 * j8 + 1] * cscale, h[j8].x, l[j8].x);
-                        f16_split2(vv[8 * j8 + 2] * cscale, vv[8 * j8 + 3] * cscale, h[j8].y, l[j8].y);
-                        f16_split2(vv[8 * j8 + 4] * cscale, vv[8 * j8 + 5] * cscale, h[j8].z, l[j8].z);
-                        f16_split2(vv[8 * j8 + 6] * cscale, vv[8 * j8 + 7] * cscale, h[j8].w, l[j8].w);
+                        f16_split2(vv[8 * j8 + 0], vv[8 * j8 + 1], h[j8].x, l[j8].x);
+                        f16_split2(vv[8 * j8 + 2], vv[8 * j8 + 3], h[j8].y, l[j8].y);
+                        f16_split2(vv[8 * j8 + 4], vv[8 * j8 + 5], h[j8].z, l[j8].z);
+                        f16_split2(vv[8 * j8 + 6], vv[8 * j8 + 7], h[j8].w, l[j8].w);
                     }
+                    if (p.store3d) {
+                        // one 3-D box {16 columns, 32 rows, hi | lo plane} per group: half as many TMA operations; the
+                        // single staging pair is free again long before the next group's maths is done
+                        if (lane == 0) bulk_wait_read0();
+                        __syncwarp();
+                        st_hi[lane * 2 + (0 ^ swz)] = h[0];
+                        st_hi[lane * 2 + (1 ^ swz)] = h[1];
+                        st_lo[lane * 2 + (0 ^ swz)] = l[0];
+                        st_lo[lane * 2 + (1 ^ swz)] = l[1];
+                        fence_proxy_async_smem();
+                        __syncwarp();
+                        if (lane == 0) { tma_store_3d(&tmC_hi, st_hi, col0 + 16 * hh, m0 + q * 32, 0); bulk_commit(); }
+                    } else {
                     // hi: wait until the previous hi store has read its buffer (the lo store issued after it may still run)
                     if (lane == 0) bulk_wait_read1();
                     __syncwarp();
@@ -444,6 +480,7 @@ f16_gemm_kk_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
                     fence_proxy_async_smem();
                     __syncwarp();
                     if (lane == 0) { tma_store_2d(&tmC_lo, st_lo, col0 + 16 * hh, m0 + q * 32); bulk_commit(); }
+                    }
                 }
             }
         }
@@ -1621,6 +1658,18 @@ int make_map16_2d(CUtensorMap* m, const __half* base, int64_t rows, int64_t cols
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(f16 2d %lld x %lld) failed: %d", (long long)rows, (long long)cols, (int)r); return PPO_ERR_CUDA; }
     return PPO_OK;
 }
+// store map over BOTH planes of an output pair: {cols, rows, 2} with the lo plane `plane_bytes` after the hi plane; box
+// {16 columns, 32 rows, 2 planes} = the 2 x 1 KB a warp stages (SWIZZLE_32B)
+int make_map16_store3d(CUtensorMap* m, const __half* hi, int64_t rows, int64_t cols, int64_t plane_bytes) {
+    cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, 2};
+    cuuint64_t strides[2] = {(cuuint64_t)cols * 2, (cuuint64_t)plane_bytes};
+    cuuint32_t box[3] = {16, 32, 2};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = g_encode16(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, (void*)hi, dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? PPO_OK : PPO_ERR_CUDA;      // (the caller falls back to two 2-D maps)
+}
 // 3-D view of a row-major [rows][cols] fp16 matrix as {64, rows, cols/64}: one box = `blocks` column blocks of
 // F_BK rows each, i.e. the canonical MN-major SWIZZLE_128B operand layout
 int make_map16_mn(CUtensorMap* m, const __half* base, int64_t rows, int64_t cols, int blocks) {
@@ -1724,9 +1773,16 @@ int launch_kk16(ppo_ctx* ctx, const __half* A, const __half* A_lo, const __half*
     PPO_TRY(make_map16_2d(&mAl, A_lo, M, K, F_BM));
     PPO_TRY(make_map16_2d(&mB, B, N, K, KK16Smem<BN, TWO>::B_ROWS));
     PPO_TRY(make_map16_2d(&mBl, B_lo, N, K, KK16Smem<BN, TWO>::B_ROWS));
-    PPO_TRY(make_map16_2d(&mC, C, M, N, 32, 16));      // store boxes: 32 rows x 16 columns (one warp's), SWIZZLE_32B
+    // store boxes: 32 rows x 16 columns (one warp's), SWIZZLE_32B; hi and lo planes in one 3-D box when the lo plane lies
+    // a whole number of rows behind the hi plane (the engine's own buffers do), else one 2-D map each
+    const int64_t plane = (int64_t)((const char*)C_lo - (const char*)C);
+    static const int no3d = getenv("PPO_F16_STORE2D") ? atoi(getenv("PPO_F16_STORE2D")) : 0;      // tuning experiments
+    bool store3d = !no3d && plane > 0 && plane % ((int64_t)N * 2) == 0 && plane % 16 == 0 && plane < ((int64_t)1 << 40) &&
+                   make_map16_store3d(&mC, C, M, N, plane) == PPO_OK;
+    if (!store3d) PPO_TRY(make_map16_2d(&mC, C, M, N, 32, 16));
     PPO_TRY(make_map16_2d(&mCl, C_lo, M, N, 32, 16));
     KK16Params p = base;
+    p.store3d = store3d ? 1 : 0;
     static const int env_chunk = getenv("PPO_F16_KK_CHUNK") ? atoi(getenv("PPO_F16_KK_CHUNK")) : 0;      // tuning experiments
     static const float env_comp = getenv("PPO_F16_RZ_COMP") ? (float)atof(getenv("PPO_F16_RZ_COMP")) : -1.0f;
     p.chunk_kb = env_chunk > 0 ? env_chunk : F_KK_CHUNK_KB;
@@ -1940,10 +1996,10 @@ int ensure_f16_workspace(ppo_policy* p, int64_t tokens) {
     if (tokens <= st->tokens) return PPO_OK;
     ppo_ctx* ctx = p->ctx;
     PPO_CUDA(cudaStreamSynchronize(ctx->stream));
-    fr(st->x_hi); fr(st->x_lo); fr(st->dz_hi[0]); fr(st->dz_hi[1]); fr(st->dz_lo[0]); fr(st->dz_lo[1]); fr(st->partial);
+    fr(st->x_hi); fr(st->x_lo); fr(st->dz_hi[0]); fr(st->dz_hi[1]); st->dz_lo[0] = st->dz_lo[1] = nullptr; fr(st->partial);      // (lo planes live in the hi allocations)
     fr(st->tok_of_row); fr(st->blk_counts);
     for (auto& a : st->act_hi) fr(a);
-    for (auto& a : st->act_lo) fr(a);
+    for (auto& a : st->act_lo) a = nullptr;
     for (auto& a : st->act_sign) fr(a);
     const int L = p->L;
     int hmax = 1;
@@ -1962,15 +2018,23 @@ int ensure_f16_workspace(ppo_policy* p, int64_t tokens) {
     };
     PPO_TRY(zalloc(&st->x_hi, (size_t)tokens * p->dims[0] * 2 + slack));
     PPO_TRY(zalloc(&st->x_lo, (size_t)tokens * p->dims[0] * 2 + slack));
+    // The hi and lo halves of an output pair are two planes of ONE allocation, the lo plane a whole number of rows (of
+    // every width the buffer is used with) behind the hi plane: the GEMM epilogues then store both with one 3-D TMA box
+    auto lcm = [](int64_t a, int64_t b) { int64_t x = a, y = b; while (y) { const int64_t t = x % y; x = y; y = t; } return a / x * b; };
+    auto pair_alloc = [&](__half** hi, __half** lo, size_t bytes, int64_t row_bytes_lcm) -> int {
+        const size_t plane = (size_t)round_up((int64_t)bytes, lcm(row_bytes_lcm, 256));
+        PPO_TRY(zalloc(hi, 2 * plane));
+        *lo = reinterpret_cast<__half*>(reinterpret_cast<char*>(*hi) + plane);
+        return PPO_OK;
+    };
+    int64_t hid_lcm = 2;
+    for (int l = 1; l < L; ++l) hid_lcm = lcm(hid_lcm, (int64_t)p->dims[l] * 2);
     for (int l = 1; l < L; ++l) {
-        PPO_TRY(zalloc(&st->act_hi[l], (size_t)tokens * p->dims[l] * 2 + slack));
-        PPO_TRY(zalloc(&st->act_lo[l], (size_t)tokens * p->dims[l] * 2 + slack));
+        PPO_TRY(pair_alloc(&st->act_hi[l], &st->act_lo[l], (size_t)tokens * p->dims[l] * 2 + slack, (int64_t)p->dims[l] * 2));
         if (l < L - 1) PPO_CUDA(cudaMalloc((void**)&st->act_sign[l], sign_words(tokens, p->dims[l]) * 4));   // (the head gates on sign(hi))
     }
-    for (int i = 0; i < 2; ++i) {
-        PPO_TRY(zalloc(&st->dz_hi[i], (size_t)tokens * hmax * 2 + slack));
-        PPO_TRY(zalloc(&st->dz_lo[i], (size_t)tokens * hmax * 2 + slack));
-    }
+    for (int i = 0; i < 2; ++i)
+        PPO_TRY(pair_alloc(&st->dz_hi[i], &st->dz_lo[i], (size_t)tokens * hmax * 2 + slack, hid_lcm));
     PPO_CUDA(cudaMalloc((void**)&st->tok_of_row, (size_t)tokens * sizeof(int)));
     PPO_CUDA(cudaMalloc((void**)&st->blk_counts, (size_t)ceil_div(tokens, TOK_PER_BLOCK) * sizeof(int)));
     if (st->d_rows == nullptr) PPO_CUDA(cudaMalloc((void**)&st->d_rows, sizeof(int)));
@@ -2240,9 +2304,9 @@ void f16_destroy(ppo_policy* p) {
     F16State* st = state(p);
     if (!st) return;
     for (auto& ly : st->layers) { fr(ly.W_hi); fr(ly.W_lo); fr(ly.WT_hi); fr(ly.WT_lo); }
-    fr(st->x_hi); fr(st->x_lo); fr(st->dz_hi[0]); fr(st->dz_hi[1]); fr(st->dz_lo[0]); fr(st->dz_lo[1]); fr(st->partial);
+    fr(st->x_hi); fr(st->x_lo); fr(st->dz_hi[0]); fr(st->dz_hi[1]); st->dz_lo[0] = st->dz_lo[1] = nullptr; fr(st->partial);      // (lo planes live in the hi allocations)
     for (auto& a : st->act_hi) fr(a);
-    for (auto& a : st->act_lo) fr(a);
+    for (auto& a : st->act_lo) a = nullptr;
     for (auto& a : st->act_sign) fr(a);
     fr(st->sc); fr(st->st); fr(st->tok_of_row); fr(st->blk_counts); fr(st->d_rows); fr(st->bar);
     delete st;

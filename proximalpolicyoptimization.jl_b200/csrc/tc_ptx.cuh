@@ -59,6 +59,12 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* s
                  "r"(smem_u32(src)), "r"(x), "r"(y)
                  : "memory");
 }
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, const void* src, int x, int y, int z) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                     reinterpret_cast<uint64_t>(m)),
+                 "r"(smem_u32(src)), "r"(x), "r"(y), "r"(z)
+                 : "memory");
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
