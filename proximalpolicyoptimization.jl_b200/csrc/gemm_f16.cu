@@ -1734,8 +1734,13 @@ size_t f16_wgrad_partial_bytes(int64_t tokens, int K, int N, int num_sms) {
     const int tiles = (int)(ceil_div(K, F_BM) * ceil_div(N, BN));
     return (size_t)wgrad_splits16(tokens, tiles, num_sms) * K * N * 4;
 }
-// row chunks of the column-sum fold (the second stage adds them serially: keep it short)
-inline int colsum_chunks(int64_t rows) { return (int)std::max<int64_t>(1, std::min<int64_t>(64, rows)); }
+// row chunks of a two-stage fold: both stages walk their rows serially (a dependent chain of L2 round trips), so the
+// chunk count balances them: ~sqrt(rows), at most 64
+inline int colsum_chunks(int64_t rows) {
+    int c = 1;
+    while ((int64_t)c * c < rows && c < 64) ++c;
+    return c;
+}
 // dgrad-epilogue column sums [4 * tiles_m][K] + the fold's scratch [64][K]
 size_t f16_colsum_partial_bytes(int64_t tokens, int K) { return ((size_t)4 * ceil_div(tokens, F_BM) + 64) * (size_t)K * 4; }
 size_t f16_partial_bytes(int64_t tokens, int K, int N, int num_sms) {
@@ -1973,7 +1978,7 @@ int head_bwd16(ppo_ctx* ctx, const __half* H_hi, const __half* H_lo, const float
     PPO_CUDA(cudaGetLastError());
     // fold the per-CTA partials [ctas][stride] in two parallel stages (a single pass over 592 partials per output is a
     // 60 us serial chain: it dominated the small-minibatch regime of the multi-GPU runs)
-    const int chunks = (int)std::min<int64_t>(64, ctas);
+    const int chunks = colsum_chunks(ctas);
     const int64_t rpc = ceil_div(ctas, chunks);
     float* scratch = partial + (size_t)ctas * stride;
     if (defer != nullptr) {
@@ -2131,7 +2136,9 @@ int f16_adam_refresh(ppo_policy* p, ppo_opt* opt, const P2PView* xv, int* d_step
         PPO_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, f16_adam_refresh_kernel, 256, 0));
         per_sm = std::max(1, std::min(4, occ));
     }
-    f16_adam_refresh_kernel<<<(unsigned)(ctx->num_sms * per_sm), 256, 0, ctx->stream>>>(a);
+    // (small policies: fewer CTAs make the two grid barriers cheaper than the work they separate)
+    const int64_t ctas = std::min<int64_t>((int64_t)ctx->num_sms * per_sm, std::max<int64_t>(32, ceil_div(p->P, 1024)));
+    f16_adam_refresh_kernel<<<(unsigned)ctas, 256, 0, ctx->stream>>>(a);
     ctx->launches += 1;
     PPO_CUDA(cudaGetLastError());
     return PPO_OK;
