@@ -420,19 +420,20 @@ def kernel_rooflines(h, cfg, B_local, gemm):
         return kernels[name]
 
     hbm("K1_scan_namedN", "scan", cfg.N, 15)
-    k1 = hbm("K1_scan_64M", "scan", 64 * 1024 * 1024, 15, iters=5)
-    k1g = hbm("K1_scan_64M_gamma0.99", "scan", 64 * 1024 * 1024, 15, 1, iters=5)
-    k2 = hbm("K1K2_scan_64M_with_norm_stats", "scan_norm", 64 * 1024 * 1024, 15, iters=5)
+    # (20 launches each: a 0.13 ms kernel timed 5 times lets one hiccup of the box halve the reported fraction)
+    k1 = hbm("K1_scan_64M", "scan", 64 * 1024 * 1024, 15, iters=20)
+    k1g = hbm("K1_scan_64M_gamma0.99", "scan", 64 * 1024 * 1024, 15, 1, iters=20)
+    k2 = hbm("K1K2_scan_64M_with_norm_stats", "scan_norm", 64 * 1024 * 1024, 15, iters=20)
     # stress variants: episodes as long as a whole scan tile (4 096 transitions: the look-ahead window
     # misses, every tile looks back one or two tiles), and ONE unterminated episode over all 64 M transitions (every
     # tile's carry depends on every tile to its right: the decoupled look-back's worst case)
     k1s = hbm("K1_scan_64M_episodes4096_gamma0.99", "scan", 64 * 1024 * 1024, 4096, 1, iters=3)
     k1l = hbm("K1_scan_64M_longepisodes_gamma0.99", "scan", 64 * 1024 * 1024, 1 << 30, 1, iters=3)
     hbm("K3_shuffle", "shuffle", cfg.N)
-    k4 = hbm("K4_gather_ldg", "gather0", cfg.N, cfg.nf * cfg.nhe, cfg.A, B_local)
+    k4 = hbm("K4_gather_ldg", "gather0", cfg.N, cfg.nf * cfg.nhe, cfg.A, B_local, iters=20)
     hbm("K4_gather_bulk", "gather1", cfg.N, cfg.nf * cfg.nhe, cfg.A, B_local)
     hbm("K6_loss_namedB", "loss", B_local, cfg.A)
-    k6 = hbm("K6_loss_1M", "loss", 1 << 20, cfg.A, iters=5)
+    k6 = hbm("K6_loss_1M", "loss", 1 << 20, cfg.A, iters=20)
     hp = "head16" if gemm == "f16x3" else "head"     # the fp16-split engine has its own head kernels
     hbm("K5_head_fwd", hp + "_fwd", M, cfg.H, cfg.apa, iters=5)
     hbm("K7_head_bwd", hp + "_bwd", M, cfg.H, cfg.apa, iters=5)

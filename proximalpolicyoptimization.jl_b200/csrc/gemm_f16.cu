@@ -411,7 +411,10 @@ f16_gemm_kk_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
                 if (p.epi == F_EPI_FWD) {
                     // v = scaled pre-activation (bias included): sign bit, leakyrelu
                     uint32_t w = 0u;
-                    if (slope_unit) {
+                    if (slope_unit && p.signs_out == nullptr) {      // (the last hidden layer: the head gates on sign(hi))
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], slope_eff * v[j]);
+                    } else if (slope_unit) {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
                             const float x = v[j];
