@@ -501,6 +501,61 @@ def ncu_traffic_probe(M, H, which="tc3_fwd"):
     return total, "ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum replay of one launch, run by bench.py"
 
 
+def ncu_step_traffic_probe(args, launches_per_step):
+    """Measured DRAM traffic of ONE WHOLE STEP (returns scan + permutation + every minibatch of the epoch): this script is
+    replayed with `--profile --steps 1 --warmup 1` under `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum` in a
+    separate process (one pass per kernel; no timing is taken from it) and the per-kernel bytes are summed over a window of
+    exactly one step's launches (the step is periodic, so any window of that length behind the one-off buffer append
+    holds every kernel of a step once)."""
+    import csv
+    import tempfile
+    ncu = shutil.which("ncu") or "/usr/local/cuda/bin/ncu"
+    if not os.path.exists(ncu):
+        return None
+    with tempfile.TemporaryDirectory() as td:
+        log_csv = os.path.join(td, "step.csv")
+        cmd = [ncu, "--metrics", "dram__bytes_read.sum,dram__bytes_write.sum", "--clock-control", "none", "--csv", "--log-file",
+               log_csv, "--launch-skip", "12", "--launch-count", str(int(launches_per_step)), sys.executable, os.path.abspath(__file__), "--profile", "--steps", "1", "--warmup", "1", "--config",
+               args.config, "--gemm", args.gemm, "--e2e-feat", args.e2e_feat, "--e2e-mask", args.e2e_mask]
+        if args.batch:
+            cmd += ["--batch", str(args.batch)]
+        env = dict(os.environ, WORLD_SIZE="1", RANK="0", LOCAL_RANK="0")
+        try:
+            subprocess.run(cmd, capture_output=True, text=True, timeout=420, env=env)
+            rows = list(csv.reader(open(log_csv)))
+        except Exception as e:   # noqa: BLE001
+            return {"error": f"ncu step probe failed: {e}"[:200]}
+    hdr = next((i for i, r in enumerate(rows) if len(r) > 5 and r[0] == "ID"), None)
+    if hdr is None:
+        return {"error": "ncu step probe: no launch list"}
+    H = rows[hdr]
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    append_only = ("narrow_to_f32", "mask_from_bits", "actions_in", "normalize_bool", "absmax_f32", "i64_to_f32")
+    rd = wr = 0.0
+    launches = 0
+    for r in rows[hdr + 1:]:
+        if len(r) < len(H):
+            continue
+        d = dict(zip(H, r))
+        if any(k in d["Kernel Name"] for k in append_only):
+            continue
+        try:
+            v = float(d["Metric Value"].replace(",", "")) * scale.get(d["Metric Unit"], 1.0)
+        except ValueError:
+            continue
+        if d["Metric Name"].startswith("dram__bytes_read"):
+            rd += v
+            launches += 1
+        elif d["Metric Name"].startswith("dram__bytes_write"):
+            wr += v
+    if launches == 0:
+        return {"error": "ncu step probe: no dram__bytes rows"}
+    return {"dram_read_gb_per_step": round(rd / 1e9, 2), "dram_write_gb_per_step": round(wr / 1e9, 2),
+            "kernel_launches_profiled": launches,
+            "source": "ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum over `bench.py --profile --steps 1 --warmup 1`, "
+                      "run by bench.py in a separate process (append kernels excluded)"}
+
+
 def run_c2(h, args, gemm_mode):
     """config C2: 65 536 transitions, Policy(72,128,2,4) on 64 half-edges (test/test_square_mesh.jl:29), at the
     reference-like tiny minibatch and at B = 4096; one GPU"""
@@ -742,6 +797,7 @@ def _run_ours(args):
                     tr = guarded("traffic", lambda: ncu_traffic_probe(B_local * cfg.nhe, cfg.H, {"fp32": "gemm_fwd", "tf32x3": "tc1_fwd", "f16x3": "tc3_fwd"}[args.gemm]))
                     if tr:
                         roofline["traffic"], roofline["traffic_source"] = tr
+                    roofline["step_traffic"] = guarded("step_traffic", lambda: ncu_step_traffic_probe(args, main["launches"] / args.steps))
             if world == 1:
                 # the CPU baseline is timed at N = 1 only (torchrun pins OMP_NUM_THREADS=1 and the ranks share the host)
                 cpu = guarded("cpu_baseline", lambda: cpu_baseline(cfg))
