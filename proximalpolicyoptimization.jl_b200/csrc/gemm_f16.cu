@@ -48,7 +48,9 @@ namespace {
 constexpr int F_BM = 128;
 constexpr int F_BK = 64;                    // 64 fp16 = one 128-byte swizzle row
 constexpr int F_STAGES = 2;
-constexpr int F_CHUNK_KB = 2;               // mn kernel: k-blocks per TMEM accumulation chain (128 elements = 24 MMAs)
+// mn kernel: k-blocks per TMEM accumulation chain (128 elements = 24 MMAs).  256-element chains were measured at 1 % faster
+// (1437 vs 1449 us sustained at M = 2^20, K = N = 512: the kernel is not drain-bound) and are not worth the accuracy margin.
+constexpr int F_CHUNK_KB = 2;
 // kk kernel: 256 elements = 48 MMAs per chain.  The two TMEM stages then hold a whole K = 512 tile of look-ahead, so
 // the MMA issuer keeps running while the epilogue warps finish the previous tile (with 128-element chains the tensor
 // pipe idled ~45 % of the time waiting for them: profiles/r01_f16_ncu.md).  The longer chain's round-toward-zero
