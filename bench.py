@@ -11,16 +11,20 @@ backward (K7) -> [gradient exchange] -> Adam (K8).
 `value` = transitions processed by all ranks / device time (CUDA events on the library's stream, max over ranks) with the
 buffer resident in HBM; `e2e` = the same through the public API with HOST (pinned) buffers, timed over the same number
 of steps: the H2D append of the whole buffer and the D2H read of the losses are inside the timed region.  The host
-features are the small integers a quad-game state holds (Matrix{Int64} in the reference), handed over as Int8 through
-ppo_buffer_append_i8 (--e2e-feat f32: as Float32, 4x the bytes).
+features are the small integers a quad-game state holds (Matrix{Int64} in the reference), handed over as Int8, the
+0 / -Inf action masks as one bit per action, through ppo_buffer_append_packed (--e2e-feat f32 / --e2e-mask f32: as
+Float32, 4x / 32x the bytes).
 N=1 workload: config C3 (1M transitions, MLP 3x512, B=65536).  N>1: every rank holds a C3-sized shard (weak scaling; at
 N=8 this IS config C4: 8M transitions in total, global B=65536, B/N rows per rank); --scaling strong runs C4 as written
 at any N (8 388 608 transitions in total, N/G per rank).  The minibatch gradients are summed over the ranks inside the Adam
 kernel through NVLink peer memory (CUDA IPC; PPO_B200_NO_P2P=1 selects the NCCL all-reduce instead).
 
 Besides the headline the line carries (each measured live in this run):
-  roofline      dominant kernel (hidden Dense forward GEMM) + roofline.hbm (scan / gather / loss fractions of the HBM peak)
-                + roofline.traffic from an ncu replay of that kernel launched by this script (null when ncu is unusable)
+  roofline      dominant kernel (hidden Dense forward GEMM): 60 back-to-back launches against the SUSTAINED bf16 peak (the
+                regime of the step), roofline.timed_alone against the burst peak; roofline.hbm (scan / gather / loss, each
+                timed alone on a settled GPU, against the HBM copy peak); roofline.traffic / roofline.step_traffic from ncu
+                replays of that kernel / of one whole step launched by this script (null when ncu is unusable)
+  config.token_compaction   the library's default (the MLP skips fully masked tokens) and the same steps with every token
   cpu_baseline  the restated CPU path (oracle port) on a bounded sample, rank 0 at N=1
   configs       the other named configs: C2 (65k transitions, Policy(72,128,2,4)) at B=32 and B=4096, C5 (disk replay)
   dp_parity     N>1: a short sharded epoch after the timed region — replicas bit-identical, losses / weights vs the
